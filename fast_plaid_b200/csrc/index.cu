@@ -1,0 +1,166 @@
+// Index handle, error reporting and workspace layout of the C ABI.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void fpb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* fpb_last_error(void) { return g_err; }
+extern "C" int fpb_abi_version(void) { return 1; }
+
+static int bitrev(int x, int nbits) {
+  int r = 0;
+  for (int k = 0; k < nbits; ++k)
+    if (x & (1 << k)) r |= 1 << (nbits - 1 - k);
+  return r;
+}
+
+extern "C" int fpb_index_create(fpb_index** out, int device, int nbits, int dim, int64_t n_centroids,
+                                const void* d_centroids, const void* d_bucket_weights,
+                                int64_t n_docs, const int64_t* d_doc_offsets,
+                                const int32_t* d_doc_codes, const uint8_t* d_doc_residuals,
+                                const int64_t* d_ivf_offsets, const int32_t* d_ivf_pids,
+                                int64_t n_ivf, int64_t max_doc_len, int64_t doc_id_base) {
+  if (!out) {
+    fpb_set_error("fpb_index_create: out is NULL");
+    return FPB_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (nbits != 2 && nbits != 4) {
+    fpb_set_error("unsupported nbits=%d (2 and 4 are supported)", nbits);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  const int pd = dim * nbits / 8;
+  if ((dim != 64 && dim != 128) || (pd != 16 && pd != 32 && pd != 64)) {
+    fpb_set_error("unsupported embedding dim=%d with nbits=%d: this build supports dim 64 and 128", dim, nbits);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  if (n_centroids <= 0 || n_docs < 0 || !d_centroids || !d_bucket_weights || !d_doc_offsets) {
+    fpb_set_error("fpb_index_create: bad sizes or NULL codec/offset pointers");
+    return FPB_ERR_INVALID;
+  }
+  if (n_docs >= (int64_t(1) << 31) || n_centroids >= (int64_t(1) << 31)) {
+    fpb_set_error("fpb_index_create: n_docs and n_centroids must fit in int32 per shard");
+    return FPB_ERR_UNSUPPORTED;
+  }
+  FPB_CUDA_CHECK(cudaSetDevice(device));
+  fpb_index* ix = new fpb_index();
+  memset(ix, 0, sizeof(*ix));
+  ix->device = device;
+  ix->nbits = nbits;
+  ix->dim = dim;
+  ix->pd = pd;
+  ix->K = n_centroids;
+  ix->N = n_docs;
+  ix->n_ivf = n_ivf;
+  ix->max_doc_len = max_doc_len;
+  ix->doc_id_base = doc_id_base;
+  ix->centroids = static_cast<const __half*>(d_centroids);
+  ix->doc_offsets = d_doc_offsets;
+  ix->doc_codes = d_doc_codes;
+  ix->doc_residuals = d_doc_residuals;
+  ix->ivf_offsets = d_ivf_offsets;
+  ix->ivf_pids = d_ivf_pids;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    delete ix;
+    fpb_set_error("cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+    return FPB_ERR_CUDA;
+  }
+  ix->sm_count = prop.multiProcessorCount;
+  uint16_t w[16];
+  e = cudaMemcpy(w, d_bucket_weights, sizeof(uint16_t) * (1 << nbits), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    delete ix;
+    fpb_set_error("copy of bucket_weights failed: %s", cudaGetErrorString(e));
+    return FPB_ERR_CUDA;
+  }
+  for (int i = 0; i < 16; ++i) ix->w_perm_bits[i] = 0;
+  for (int i = 0; i < (1 << nbits); ++i) ix->w_perm_bits[i] = w[bitrev(i, nbits)];
+  int64_t n_tokens = 0;
+  if (n_docs > 0) {
+    e = cudaMemcpy(&n_tokens, d_doc_offsets + n_docs, sizeof(int64_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      delete ix;
+      fpb_set_error("copy of doc_offsets[N] failed: %s", cudaGetErrorString(e));
+      return FPB_ERR_CUDA;
+    }
+  }
+  ix->E = n_tokens;
+  *out = ix;
+  return FPB_OK;
+}
+
+extern "C" void fpb_index_destroy(fpb_index* index) { delete index; }
+
+extern "C" int fpb_workspace_layout(const fpb_index* ix, int B, int Q, const fpb_params* p,
+                                    fpb_layout* L) {
+  if (!ix || !p || !L) {
+    fpb_set_error("fpb_workspace_layout: NULL argument");
+    return FPB_ERR_INVALID;
+  }
+  if (B <= 0 || Q <= 0) {
+    fpb_set_error("fpb_workspace_layout: B=%d Q=%d must be positive", B, Q);
+    return FPB_ERR_INVALID;
+  }
+  if (Q > 256) {
+    fpb_set_error("queries with more than 256 tokens are not supported (Q=%d)", Q);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  if (p->n_ivf_probe < 1 || p->n_ivf_probe > 32) {
+    fpb_set_error("n_ivf_probe=%d outside the supported range [1,32]", p->n_ivf_probe);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  if (p->n_full_scores < 1 || p->top_k < 1) {
+    fpb_set_error("n_full_scores and top_k must be >= 1");
+    return FPB_ERR_INVALID;
+  }
+  int R = p->n_full_scores / 4;
+  if (R < 1) R = 1;
+  if (R > 4096) {
+    fpb_set_error("n_full_scores=%d: more than 4096 re-ranked documents per query is not supported",
+                  p->n_full_scores);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  memset(L, 0, sizeof(*L));
+  int Qp = fpb_next_pow2(Q < 16 ? 16 : Q);
+  L->B = B;
+  L->Q = Q;
+  L->Qp = Qp;
+  L->n_tiles = int((ix->K + 127) / 128);
+  L->R = R;
+  L->n_probe = p->n_ivf_probe;
+  L->cand_cap = int(ix->N > 0 ? ix->N : 1);
+  L->bitmap_words = int((ix->N + 31) / 32) + 1;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    int64_t o = off;
+    off += fpb_align256(bytes);
+    return o;
+  };
+  L->off_queries = take(int64_t(B) * Qp * ix->dim * 2);
+  L->off_S = take(int64_t(B) * ix->K * Qp * 2);
+  L->off_tmax = take(int64_t(B) * Qp * L->n_tiles * 2);
+  L->off_cells = take(int64_t(B) * Q * L->n_probe * 4);
+  L->off_bitmap = take(int64_t(B) * L->bitmap_words * 4);
+  L->off_n_cand = take(int64_t(B) * 4);
+  L->off_cand = take(int64_t(B) * L->cand_cap * 4);
+  L->off_approx = take(int64_t(B) * L->cand_cap * 4);
+  L->off_work = take(int64_t(B + 8) * 4);
+  L->off_n_rerank = take(int64_t(B) * 4);
+  L->off_rerank = take(int64_t(B) * R * 4);
+  L->off_rerank_approx = take(int64_t(B) * R * 4);
+  L->off_exact = take(int64_t(B) * R * 4);
+  L->total_bytes = off;
+  return FPB_OK;
+}

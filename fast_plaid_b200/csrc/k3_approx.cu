@@ -1,0 +1,262 @@
+// K3  : approximate (centroid-only) document scores                       (search.rs:554-592)
+//         approx[d] = sum_{q<Q}^{fp32}  max_{t<len(d)}  S[b][code[d,t]][q]     (fp16 max)
+// K3b : pruning to the n_full_scores/4 best candidates                     (search.rs:602-619)
+//
+// The reference gathers S rows into a [tokens, Q] tensor, pads it to [2000, maxlen, Q],
+// masks, maxes and sums, 128 times per query with two host syncs each.  Here one warp walks
+// one candidate document: 32 codes are read with one coalesced load, each S row (Qp fp16 =
+// LPR x 16 B) is fetched by LPR adjacent lanes so a warp-wide load touches 32/LPR distinct
+// rows (one L1 wavefront per row instead of four), and the running maxima stay in registers.
+// The stage is bound by L2 gather bandwidth (Qp*2 bytes per token per query); the codes
+// stream from HBM once per (query, candidate).
+#include "kernels.h"
+
+namespace {
+
+constexpr int K3_THREADS = 256;
+constexpr int K3_DOCS_PER_CHUNK = 64;
+
+__global__ void k3_prefix_kernel(const int32_t* __restrict__ n_cand, int B, int32_t* __restrict__ work) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      work[b] = acc;
+      acc += (n_cand[b] + K3_DOCS_PER_CHUNK - 1) / K3_DOCS_PER_CHUNK;
+    }
+    work[B] = acc;
+    work[B + 1] = 0;  // dynamic work counter
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(K3_THREADS)
+k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
+                 const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
+                 const int32_t* __restrict__ n_cand, int32_t* __restrict__ work, int B,
+                 float* __restrict__ approx) {
+  constexpr int QP = LPR * 8;
+  constexpr int TPI = 32 / LPR;
+  __shared__ int s_b, s_c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const __half2 sentinel = __float2half2_rn(FPB_PAD_SENTINEL);
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const int c = atomicAdd(&work[B + 1], 1);
+      if (c >= work[B]) {
+        s_b = -1;
+      } else {
+        int lo = 0, hi = B - 1;  // largest b with work[b] <= c
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (work[mid] <= c) lo = mid; else hi = mid - 1;
+        }
+        s_b = lo;
+        s_c = c - work[lo];
+      }
+    }
+    __syncthreads();
+    const int b = s_b;
+    if (b < 0) return;
+    const int n = n_cand[b];
+    const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP);
+    const int32_t* cb = cand + int64_t(b) * cand_cap;
+    float* ab = approx + int64_t(b) * cand_cap;
+
+    for (int i = 0; i < K3_DOCS_PER_CHUNK / 8; ++i) {
+      const int idx = s_c * K3_DOCS_PER_CHUNK + i * 8 + warp;
+      if (idx >= n) break;
+      const int d = cb[idx];
+      const int64_t o0 = doc_offsets[d];
+      const int len = int(doc_offsets[d + 1] - o0);
+      __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
+      for (int base = 0; base < len; base += 32) {
+        const int t = base + lane;
+        const int code = (t < len) ? __ldg(codes + o0 + t) : -1;
+#pragma unroll
+        for (int j = 0; j < LPR; ++j) {
+          const int c = __shfl_sync(0xffffffffu, code, j * TPI + grp);
+          if (c >= 0) {
+            const uint4 v = __ldg(Sb + int64_t(c) * LPR + sub);
+            m0 = __hmax2(m0, u32_as_half2(v.x));
+            m1 = __hmax2(m1, u32_as_half2(v.y));
+            m2 = __hmax2(m2, u32_as_half2(v.z));
+            m3 = __hmax2(m3, u32_as_half2(v.w));
+          }
+        }
+      }
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) {
+        m0 = __hmax2(m0, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m0), off)));
+        m1 = __hmax2(m1, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m1), off)));
+        m2 = __hmax2(m2, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m2), off)));
+        m3 = __hmax2(m3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m3), off)));
+      }
+      // fp32 sum over the real query tokens (sum_dim_intlist(.., Kind::Float), search.rs:401)
+      const int col0 = sub * 8;
+      float s = 0.f;
+      const float2 f0 = __half22float2(m0), f1 = __half22float2(m1), f2 = __half22float2(m2),
+                   f3 = __half22float2(m3);
+      if (col0 + 0 < Q) s += f0.x;
+      if (col0 + 1 < Q) s += f0.y;
+      if (col0 + 2 < Q) s += f1.x;
+      if (col0 + 3 < Q) s += f1.y;
+      if (col0 + 4 < Q) s += f2.x;
+      if (col0 + 5 < Q) s += f2.y;
+      if (col0 + 6 < Q) s += f3.x;
+      if (col0 + 7 < Q) s += f3.y;
+#pragma unroll
+      for (int off = 1; off < LPR; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) ab[idx] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3b: top-n_dec by (approx desc, candidate index asc) -- candidate index order is doc id
+// order, so this is the canonical rule "larger score, then smaller doc id".  Equivalent to
+// the reference's topk(n_full) followed by topk(n_full/4) up to tie order.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t approx_key(float a, uint32_t i) {
+  return (uint64_t(f32_key(a)) << 32) | uint64_t(0xffffffffu - i);
+}
+
+__global__ void __launch_bounds__(1024)
+k3b_select_kernel(const float* __restrict__ approx, const int32_t* __restrict__ cand, int cand_cap,
+                  const int32_t* __restrict__ n_cand, int n_dec, int Rp2, int32_t* __restrict__ rerank,
+                  float* __restrict__ rerank_approx, int32_t* __restrict__ n_rerank) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ int hist[256];
+  __shared__ int s_need, s_hd, s_cnt;
+  __shared__ uint64_t s_prefix, s_mask;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int n = n_cand[b];
+  const float* ab = approx + int64_t(b) * cand_cap;
+  const int32_t* cb = cand + int64_t(b) * cand_cap;
+  int32_t* rr = rerank + int64_t(b) * n_dec;
+  float* ra = rerank_approx + int64_t(b) * n_dec;
+  if (n <= n_dec) {  // search.rs:605 / :615 conditions false: nothing is pruned
+    for (int i = tid; i < n; i += 1024) {
+      rr[i] = cb[i];
+      ra[i] = ab[i];
+    }
+    if (tid == 0) n_rerank[b] = n;
+    return;
+  }
+  if (tid == 0) {
+    s_need = n_dec;
+    s_prefix = 0;
+    s_mask = 0;
+  }
+  const int n_up = (n + 1023) & ~1023;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const uint64_t prefix = s_prefix, mask = s_mask;
+    for (int i = tid; i < n_up; i += 1024) {
+      const bool valid = i < n;
+      const uint64_t key = valid ? approx_key(ab[i], uint32_t(i)) : 0ull;
+      const bool in = valid && ((key & mask) == prefix);
+      const unsigned act = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        const int bin = int((key >> shift) & 255ull);
+        const unsigned peers = __match_any_sync(act, bin);
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_need, cum = 0, d = 255;
+      for (; d > 0; --d) {
+        const int h = hist[d];
+        if (cum + h >= need) break;
+        cum += h;
+      }
+      s_need = need - cum;
+      s_hd = hist[d];
+      s_prefix = prefix | (uint64_t(d) << shift);
+      s_mask = mask | (255ull << shift);
+    }
+    __syncthreads();
+    if (s_hd == s_need) break;  // the whole bucket is selected
+  }
+  const uint64_t T = s_prefix;  // unprocessed low bits are zero
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) {
+    const uint64_t key = approx_key(ab[i], uint32_t(i));
+    if (key >= T) {
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < Rp2) keys[pos] = key;
+    }
+  }
+  __syncthreads();
+  const int cnt = min(s_cnt, Rp2);
+  for (int i = cnt + tid; i < Rp2; i += 1024) keys[i] = 0ull;
+  __syncthreads();
+  for (int k = 2; k <= Rp2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < Rp2; i += 1024) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const uint64_t x = keys[i], y = keys[ixj];
+          if ((x < y) == up) {
+            keys[i] = y;
+            keys[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = tid; r < n_dec; r += 1024) {
+    const uint32_t idx = 0xffffffffu - uint32_t(keys[r]);
+    rr[r] = cb[idx];
+    ra[r] = ab[idx];
+  }
+  if (tid == 0) n_rerank[b] = n_dec;
+}
+
+template <int LPR>
+int launch_k3_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
+  const int blocks = ix->sm_count * 8;
+  k3_approx_kernel<LPR><<<blocks, K3_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes,
+                                                       ws.cand(), L.cand_cap, ws.n_cand(), ws.work(), L.B,
+                                                       ws.approx());
+  FPB_LAUNCH_CHECK("k3_approx");
+  return FPB_OK;
+}
+
+}  // namespace
+
+int launch_approx(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
+  k3_prefix_kernel<<<1, 32, 0, st>>>(ws.n_cand(), L.B, ws.work());
+  FPB_LAUNCH_CHECK("k3_prefix");
+  switch (L.Qp / 8) {
+    case 2: return launch_k3_t<2>(ix, ws, st);
+    case 4: return launch_k3_t<4>(ix, ws, st);
+    case 8: return launch_k3_t<8>(ix, ws, st);
+    case 16: return launch_k3_t<16>(ix, ws, st);
+    case 32: return launch_k3_t<32>(ix, ws, st);
+    default:
+      fpb_set_error("approx scoring: unsupported padded query length %d", L.Qp);
+      return FPB_ERR_UNSUPPORTED;
+  }
+}
+
+int launch_select(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+  (void)ix;
+  const fpb_layout& L = *ws.L;
+  const int Rp2 = fpb_next_pow2(L.R);
+  k3b_select_kernel<<<L.B, 1024, size_t(Rp2) * 8, st>>>(ws.approx(), ws.cand(), L.cand_cap, ws.n_cand(),
+                                                       L.R, Rp2, ws.rerank(), ws.rerank_approx(),
+                                                       ws.n_rerank());
+  FPB_LAUNCH_CHECK("k3b_select");
+  return FPB_OK;
+}

@@ -1,0 +1,32 @@
+// Internal launchers (one per pipeline stage).  All are asynchronous on `stream`.
+#pragma once
+#include "common.cuh"
+
+struct Ws {
+  const fpb_layout* L;
+  char* base;
+  __half* queries() const { return reinterpret_cast<__half*>(base + L->off_queries); }
+  __half* S() const { return reinterpret_cast<__half*>(base + L->off_S); }
+  __half* tmax() const { return reinterpret_cast<__half*>(base + L->off_tmax); }
+  int32_t* cells() const { return reinterpret_cast<int32_t*>(base + L->off_cells); }
+  uint32_t* bitmap() const { return reinterpret_cast<uint32_t*>(base + L->off_bitmap); }
+  int32_t* n_cand() const { return reinterpret_cast<int32_t*>(base + L->off_n_cand); }
+  int32_t* cand() const { return reinterpret_cast<int32_t*>(base + L->off_cand); }
+  float* approx() const { return reinterpret_cast<float*>(base + L->off_approx); }
+  int32_t* work() const { return reinterpret_cast<int32_t*>(base + L->off_work); }
+  int32_t* n_rerank() const { return reinterpret_cast<int32_t*>(base + L->off_n_rerank); }
+  int32_t* rerank() const { return reinterpret_cast<int32_t*>(base + L->off_rerank); }
+  float* rerank_approx() const { return reinterpret_cast<float*>(base + L->off_rerank_approx); }
+  float* exact() const { return reinterpret_cast<float*>(base + L->off_exact); }
+};
+
+int launch_pad_queries(const fpb_index* ix, const Ws& ws, const __half* d_queries, cudaStream_t st);
+int launch_centroid_scores(const fpb_index* ix, const Ws& ws, cudaStream_t st);   // K1
+int launch_probe(const fpb_index* ix, const Ws& ws, cudaStream_t st);             // K1b
+int launch_candidates(const fpb_index* ix, const Ws& ws, cudaStream_t st);        // K2
+int launch_approx(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3
+int launch_select(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3b
+int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K5
+int launch_rank(const fpb_index* ix, const Ws& ws, int top_k, int64_t* d_out_ids, float* d_out_scores,
+                int32_t* d_out_counts, cudaStream_t st);                          // K6
+int launch_emit_records(const fpb_index* ix, const Ws& ws, fpb_record* d_records, cudaStream_t st);

@@ -1,0 +1,161 @@
+// Whole-batch search pipeline behind the C ABI (replaces pysearch -> search_many -> search,
+// rust/lib.rs:195-223, rust/search/search.rs:219-288, :471-696).  One stream, no host
+// synchronisation between the stages: every intermediate size is bounded up front
+// (<= Q*n_ivf_probe cells, <= N candidates, <= n_full_scores/4 re-ranked documents).
+#include "kernels.h"
+
+namespace {
+
+int prepare(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws, size_t ws_bytes,
+            fpb_layout* L, bool need_ivf) {
+  if (!ix || !p || !d_ws) {
+    fpb_set_error("search: NULL index, params or workspace");
+    return FPB_ERR_INVALID;
+  }
+  if (need_ivf && !ix->ivf_offsets) {
+    // same text as rust/search/search.rs:227-232
+    fpb_set_error(
+        "This index was built with compress_only=True and does not support search. "
+        "Rebuild with compress_only=False to enable search.");
+    return FPB_ERR_NO_IVF;
+  }
+  const int rc = fpb_workspace_layout(ix, B, Q, p, L);
+  if (rc != FPB_OK) return rc;
+  if (size_t(L->total_bytes) > ws_bytes) {
+    fpb_set_error("workspace too small: need %lld bytes, have %zu", (long long)L->total_bytes, ws_bytes);
+    return FPB_ERR_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) {
+    fpb_set_error("workspace must be 256-byte aligned");
+    return FPB_ERR_INVALID;
+  }
+  FPB_CUDA_CHECK(cudaSetDevice(ix->device));
+  return FPB_OK;
+}
+
+#define FPB_TRY(expr)            \
+  do {                           \
+    const int _rc = (expr);      \
+    if (_rc != FPB_OK) return _rc; \
+  } while (0)
+
+int run_until_maxsim(const fpb_index* ix, const Ws& ws, const __half* d_queries, cudaStream_t st) {
+  FPB_TRY(launch_pad_queries(ix, ws, d_queries, st));
+  FPB_TRY(launch_centroid_scores(ix, ws, st));
+  FPB_TRY(launch_probe(ix, ws, st));
+  FPB_TRY(launch_candidates(ix, ws, st));
+  FPB_TRY(launch_approx(ix, ws, st));
+  FPB_TRY(launch_select(ix, ws, st));
+  FPB_TRY(launch_maxsim(ix, ws, st));
+  return FPB_OK;
+}
+
+}  // namespace
+
+extern "C" int fpb_search_batch(const fpb_index* ix, const void* d_queries, int B, int Q,
+                                const fpb_params* p, void* d_ws, size_t ws_bytes, int64_t* d_out_ids,
+                                float* d_out_scores, int32_t* d_out_counts, void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, true));
+  if (!d_queries || !d_out_ids || !d_out_scores || !d_out_counts) {
+    fpb_set_error("fpb_search_batch: NULL query or output pointer");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  FPB_TRY(run_until_maxsim(ix, ws, static_cast<const __half*>(d_queries), st));
+  FPB_TRY(launch_rank(ix, ws, p->top_k, d_out_ids, d_out_scores, d_out_counts, st));
+  return FPB_OK;
+}
+
+extern "C" int fpb_search_batch_host(const fpb_index* ix, const void* h_queries, int B, int Q,
+                                     const fpb_params* p, void* d_ws, size_t ws_bytes, void* d_queries_staging,
+                                     int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts,
+                                     int64_t* h_out_ids, float* h_out_scores, int32_t* h_out_counts,
+                                     void* stream) {
+  if (!ix || !p || !h_queries || !d_queries_staging || !h_out_ids || !h_out_scores || !h_out_counts) {
+    fpb_set_error("fpb_search_batch_host: NULL pointer");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FPB_CUDA_CHECK(cudaSetDevice(ix->device));
+  FPB_CUDA_CHECK(cudaMemcpyAsync(d_queries_staging, h_queries, size_t(B) * Q * ix->dim * 2,
+                                 cudaMemcpyHostToDevice, st));
+  FPB_TRY(fpb_search_batch(ix, d_queries_staging, B, Q, p, d_ws, ws_bytes, d_out_ids, d_out_scores,
+                           d_out_counts, stream));
+  const size_t n = size_t(B) * p->top_k;
+  FPB_CUDA_CHECK(cudaMemcpyAsync(h_out_ids, d_out_ids, n * 8, cudaMemcpyDeviceToHost, st));
+  FPB_CUDA_CHECK(cudaMemcpyAsync(h_out_scores, d_out_scores, n * 4, cudaMemcpyDeviceToHost, st));
+  FPB_CUDA_CHECK(cudaMemcpyAsync(h_out_counts, d_out_counts, size_t(B) * 4, cudaMemcpyDeviceToHost, st));
+  FPB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return FPB_OK;
+}
+
+extern "C" int fpb_search_shard(const fpb_index* ix, const void* d_queries, int B, int Q,
+                                const fpb_params* p, void* d_ws, size_t ws_bytes, fpb_record* d_records,
+                                void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, true));
+  if (!d_queries || !d_records) {
+    fpb_set_error("fpb_search_shard: NULL query or record pointer");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  FPB_TRY(run_until_maxsim(ix, ws, static_cast<const __half*>(d_queries), st));
+  FPB_TRY(launch_emit_records(ix, ws, d_records, st));
+  return FPB_OK;
+}
+
+// ---- stage-level entry points ----------------------------------------------------------
+#define FPB_STAGE_PROLOGUE(need_ivf)                                   \
+  fpb_layout L;                                                        \
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, need_ivf));         \
+  cudaStream_t st = static_cast<cudaStream_t>(stream);                 \
+  Ws ws{&L, static_cast<char*>(d_ws)};
+
+extern "C" int fpb_stage_centroid_scores(const fpb_index* ix, const void* d_queries, int B, int Q,
+                                         const fpb_params* p, void* d_ws, size_t ws_bytes, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  if (!d_queries) {
+    fpb_set_error("fpb_stage_centroid_scores: NULL queries");
+    return FPB_ERR_INVALID;
+  }
+  FPB_TRY(launch_pad_queries(ix, ws, static_cast<const __half*>(d_queries), st));
+  return launch_centroid_scores(ix, ws, st);
+}
+extern "C" int fpb_stage_probe(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                               size_t ws_bytes, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  return launch_probe(ix, ws, st);
+}
+extern "C" int fpb_stage_candidates(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                                    size_t ws_bytes, void* stream) {
+  FPB_STAGE_PROLOGUE(true)
+  return launch_candidates(ix, ws, st);
+}
+extern "C" int fpb_stage_approx(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                                size_t ws_bytes, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  return launch_approx(ix, ws, st);
+}
+extern "C" int fpb_stage_select(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                                size_t ws_bytes, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  return launch_select(ix, ws, st);
+}
+extern "C" int fpb_stage_maxsim(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                                size_t ws_bytes, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  return launch_maxsim(ix, ws, st);
+}
+extern "C" int fpb_stage_rank(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                              size_t ws_bytes, int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts,
+                              void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  if (!d_out_ids || !d_out_scores || !d_out_counts) {
+    fpb_set_error("fpb_stage_rank: NULL output pointer");
+    return FPB_ERR_INVALID;
+  }
+  return launch_rank(ix, ws, p->top_k, d_out_ids, d_out_scores, d_out_counts, st);
+}

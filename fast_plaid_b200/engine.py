@@ -1,0 +1,563 @@
+"""ctypes binding of ``libfastplaid_b200.so`` (C ABI in ``include/fastplaid_b200.h``).
+
+This is the only bridge between the Python host and the CUDA kernels.  There is no CPU
+fallback: if the shared library is missing or CUDA is unavailable every entry point raises.
+PyTorch is used for device memory, streams and (in the sharded mode) ``torch.distributed``.
+
+Reference counterpart: the PyO3 module ``fast_plaid.fast_plaid_rust`` (rust/lib.rs:366-383):
+``construct_index`` -> :class:`DeviceIndex`, ``pysearch`` -> :meth:`DeviceIndex.search`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+import os
+import threading
+from typing import Any
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libfastplaid_b200.so")
+_lib = None
+_lib_lock = threading.Lock()
+
+FPB_OK = 0
+FPB_ERR_INVALID = -1
+FPB_ERR_CUDA = -2
+FPB_ERR_UNSUPPORTED = -3
+FPB_ERR_WORKSPACE = -4
+FPB_ERR_NO_IVF = -5
+
+
+class EngineUnavailableError(RuntimeError):
+    """The CUDA extension is missing or unusable.  There is deliberately no fallback."""
+
+
+class FpbParams(ctypes.Structure):
+    _fields_ = [
+        ("n_ivf_probe", ctypes.c_int32),
+        ("n_full_scores", ctypes.c_int32),
+        ("top_k", ctypes.c_int32),
+        ("batch_size", ctypes.c_int32),
+    ]
+
+
+class FpbLayout(ctypes.Structure):
+    _fields_ = [
+        ("total_bytes", ctypes.c_int64),
+        ("B", ctypes.c_int32),
+        ("Q", ctypes.c_int32),
+        ("Qp", ctypes.c_int32),
+        ("n_tiles", ctypes.c_int32),
+        ("R", ctypes.c_int32),
+        ("n_probe", ctypes.c_int32),
+        ("cand_cap", ctypes.c_int32),
+        ("bitmap_words", ctypes.c_int32),
+        ("off_queries", ctypes.c_int64),
+        ("off_S", ctypes.c_int64),
+        ("off_tmax", ctypes.c_int64),
+        ("off_cells", ctypes.c_int64),
+        ("off_bitmap", ctypes.c_int64),
+        ("off_n_cand", ctypes.c_int64),
+        ("off_cand", ctypes.c_int64),
+        ("off_approx", ctypes.c_int64),
+        ("off_work", ctypes.c_int64),
+        ("off_n_rerank", ctypes.c_int64),
+        ("off_rerank", ctypes.c_int64),
+        ("off_rerank_approx", ctypes.c_int64),
+        ("off_exact", ctypes.c_int64),
+    ]
+
+
+# every symbol include/fastplaid_b200.h declares (checked by tests/test_cabi.py)
+EXPORTED_SYMBOLS = [
+    "fpb_last_error",
+    "fpb_abi_version",
+    "fpb_index_create",
+    "fpb_index_destroy",
+    "fpb_workspace_layout",
+    "fpb_search_batch",
+    "fpb_search_batch_host",
+    "fpb_stage_centroid_scores",
+    "fpb_stage_probe",
+    "fpb_stage_candidates",
+    "fpb_stage_approx",
+    "fpb_stage_select",
+    "fpb_stage_maxsim",
+    "fpb_stage_rank",
+    "fpb_search_shard",
+    "fpb_merge_shards",
+    "fpb_reconstruct",
+    "fpb_token_scores",
+]
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the C-ABI library (no CUDA call is made)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise EngineUnavailableError(
+                f"{_LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"or `make -C fast_plaid_b200/csrc`. The engine has no CPU fallback."
+            )
+        lib = ctypes.CDLL(_LIB_PATH)
+        vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+        lib.fpb_last_error.restype = ctypes.c_char_p
+        lib.fpb_last_error.argtypes = []
+        lib.fpb_abi_version.restype = i32
+        lib.fpb_index_create.restype = i32
+        lib.fpb_index_create.argtypes = [
+            ctypes.POINTER(vp), i32, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64,
+        ]
+        lib.fpb_index_destroy.restype = None
+        lib.fpb_index_destroy.argtypes = [vp]
+        lib.fpb_workspace_layout.restype = i32
+        lib.fpb_workspace_layout.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), ctypes.POINTER(FpbLayout)]
+        lib.fpb_search_batch.restype = i32
+        lib.fpb_search_batch.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp, vp, vp]
+        lib.fpb_search_batch_host.restype = i32
+        lib.fpb_search_batch_host.argtypes = [
+            vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp, vp, vp, vp, vp, vp, vp,
+        ]
+        lib.fpb_stage_centroid_scores.restype = i32
+        lib.fpb_stage_centroid_scores.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
+        for name in ("fpb_stage_probe", "fpb_stage_candidates", "fpb_stage_approx", "fpb_stage_select",
+                     "fpb_stage_maxsim"):
+            fn = getattr(lib, name)
+            fn.restype = i32
+            fn.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
+        lib.fpb_stage_rank.restype = i32
+        lib.fpb_stage_rank.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp, vp, vp]
+        lib.fpb_search_shard.restype = i32
+        lib.fpb_search_shard.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
+        lib.fpb_merge_shards.restype = i32
+        lib.fpb_merge_shards.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
+        lib.fpb_reconstruct.restype = i32
+        lib.fpb_reconstruct.argtypes = [vp, vp, i32, vp, vp, vp]
+        lib.fpb_token_scores.restype = i32
+        lib.fpb_token_scores.argtypes = [vp, vp, i32, vp, vp, i32, i64, vp, vp]
+        _lib = lib
+        return lib
+
+
+def _check(rc: int) -> None:
+    if rc == FPB_OK:
+        return
+    msg = load_library().fpb_last_error().decode("utf-8", "replace")
+    if rc in (FPB_ERR_INVALID, FPB_ERR_NO_IVF, FPB_ERR_UNSUPPORTED):
+        raise ValueError(msg)  # anyhow -> PyValueError in the reference (rust/utils/errors.rs:5-7)
+    raise RuntimeError(msg)
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise EngineUnavailableError(
+            "fast_plaid_b200 needs a CUDA device (B200, sm_100a); there is no CPU search path."
+        )
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+@dataclasses.dataclass
+class IndexTensors:
+    """The immutable tensors of one index (or one document shard), any device.
+
+    Mirrors what ``construct_index`` receives (rust/search/load.rs:122-186).  ``doc_codes``
+    may be int64 (on-disk dtype) or int32; ``ivf`` likewise.
+    """
+
+    nbits: int
+    centroids: torch.Tensor  # [K, D] float
+    bucket_weights: torch.Tensor  # [2**nbits]
+    doc_lengths: torch.Tensor  # [N] int
+    doc_codes: torch.Tensor  # [E] int
+    doc_residuals: torch.Tensor  # [E, D*nbits/8] uint8
+    ivf: torch.Tensor | None  # [n_ivf] int (doc ids, ascending within a list)
+    ivf_lengths: torch.Tensor | None  # [K] int
+    avg_residual: torch.Tensor | None = None  # unused at search time (load.rs:146)
+    bucket_cutoffs: torch.Tensor | None = None  # unused at search time (load.rs:148)
+
+    @property
+    def num_documents(self) -> int:
+        return int(self.doc_lengths.shape[0])
+
+    @property
+    def dim(self) -> int:
+        return int(self.centroids.shape[1])
+
+
+def shard_tensors(data: IndexTensors, rank: int, world: int) -> tuple[IndexTensors, int]:
+    """Contiguous document-range shard ``rank`` of ``world``.
+
+    Centroids and bucket weights are replicated; codes/residual rows are a contiguous slice;
+    the IVF is rebuilt for the local id range (lists stay ascending because the global lists
+    are ascending, create.rs:118-124).  Returns (shard, doc_id_base).
+    """
+    n = data.num_documents
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    lens = data.doc_lengths.to(torch.int64).cpu()
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    t0, t1 = int(offs[lo]), int(offs[hi])
+    ivf = ivf_lengths = None
+    if data.ivf is not None:
+        g_ivf = data.ivf.to(torch.int64).cpu()
+        g_len = data.ivf_lengths.to(torch.int64).cpu()
+        cell_of = torch.repeat_interleave(torch.arange(g_len.shape[0], dtype=torch.int64), g_len)
+        keep = (g_ivf >= lo) & (g_ivf < hi)
+        ivf = (g_ivf[keep] - lo).to(torch.int32)
+        ivf_lengths = torch.bincount(cell_of[keep], minlength=g_len.shape[0]).to(torch.int64)
+    shard = IndexTensors(
+        nbits=data.nbits,
+        centroids=data.centroids,
+        bucket_weights=data.bucket_weights,
+        doc_lengths=lens[lo:hi],
+        doc_codes=data.doc_codes[t0:t1],
+        doc_residuals=data.doc_residuals[t0:t1],
+        ivf=ivf,
+        ivf_lengths=ivf_lengths,
+    )
+    return shard, lo
+
+
+class DeviceIndex:
+    """One index (or shard) resident in HBM + its ``fpb_index`` handle."""
+
+    def __init__(self, data: IndexTensors, device: str | torch.device, doc_id_base: int = 0) -> None:
+        _require_cuda()
+        self._lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError(f"Unsupported device string: '{device}' (the B200 engine runs on CUDA only)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        dev = self.device
+        self.nbits = int(data.nbits)
+        self.dim = data.dim
+        self.doc_id_base = int(doc_id_base)
+        with torch.cuda.device(dev):
+            # codec tensors are cast to fp16 exactly as construct_index does (load.rs:145-152)
+            self.centroids = data.centroids.to(dev, torch.float16).contiguous()
+            self.bucket_weights = data.bucket_weights.to(dev, torch.float16).contiguous()
+            lens = data.doc_lengths.to(torch.int64)
+            self.num_documents = int(lens.shape[0])
+            self.max_doc_len = int(lens.max()) if self.num_documents > 0 else 0
+            offs = torch.zeros(self.num_documents + 1, dtype=torch.int64)
+            offs[1:] = lens.cpu().cumsum(0)
+            self.num_tokens = int(offs[-1])
+            self.doc_offsets = offs.to(dev)
+            # rows past the last document (the reference's tail padding, load.py:298-300) are dropped
+            self.doc_codes = data.doc_codes[: self.num_tokens].to(dev, torch.int32).contiguous()
+            self.doc_residuals = data.doc_residuals[: self.num_tokens].to(dev, torch.uint8).contiguous()
+            if self.doc_codes.numel() == 0:
+                self.doc_codes = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.doc_residuals = torch.zeros((1, self.dim * self.nbits // 8), dtype=torch.uint8, device=dev)
+            self.num_centroids = int(self.centroids.shape[0])
+            if data.ivf is not None and data.ivf_lengths is not None:
+                il = data.ivf_lengths.to(torch.int64).cpu()
+                if il.shape[0] < self.num_centroids:
+                    il = torch.cat([il, torch.zeros(self.num_centroids - il.shape[0], dtype=torch.int64)])
+                io = torch.zeros(il.shape[0] + 1, dtype=torch.int64)
+                io[1:] = il.cumsum(0)
+                self.ivf_offsets = io.to(dev)
+                self.ivf_pids = data.ivf.to(dev, torch.int32).contiguous()
+                if self.ivf_pids.numel() == 0:
+                    self.ivf_pids = torch.zeros(1, dtype=torch.int32, device=dev)
+                n_ivf = int(io[-1])
+            else:
+                self.ivf_offsets = None
+                self.ivf_pids = None
+                n_ivf = 0
+            handle = ctypes.c_void_p()
+            _check(
+                self._lib.fpb_index_create(
+                    ctypes.byref(handle), dev.index, self.nbits, self.dim, self.num_centroids,
+                    _ptr(self.centroids), _ptr(self.bucket_weights), self.num_documents,
+                    _ptr(self.doc_offsets), _ptr(self.doc_codes), _ptr(self.doc_residuals),
+                    _ptr(self.ivf_offsets), _ptr(self.ivf_pids), n_ivf, self.max_doc_len, self.doc_id_base,
+                )
+            )
+        self._handle = handle
+        self._ws: dict[tuple, FpbLayout] = {}
+        self._buf: torch.Tensor | None = None
+        self._io: dict[tuple, dict[str, torch.Tensor]] = {}
+        self._lock = threading.Lock()
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.fpb_index_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+        self._ws = {}
+        self._buf = None
+        self._io = {}
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def has_ivf(self) -> bool:
+        return self.ivf_offsets is not None
+
+    # -- helpers -------------------------------------------------------------------------
+    @staticmethod
+    def make_params(top_k: int, n_full_scores: int, n_ivf_probe: int, batch_size: int = 2000) -> FpbParams:
+        return FpbParams(int(n_ivf_probe), int(n_full_scores), int(top_k), int(batch_size))
+
+    def layout(self, B: int, Q: int, params: FpbParams) -> FpbLayout:
+        lay = FpbLayout()
+        _check(self._lib.fpb_workspace_layout(self._handle, B, Q, ctypes.byref(params), ctypes.byref(lay)))
+        return lay
+
+    def workspace(self, B: int, Q: int, params: FpbParams) -> tuple[torch.Tensor, FpbLayout]:
+        """One grow-only device buffer per index, carved up by fpb_workspace_layout."""
+        key = (B, Q, params.n_ivf_probe, params.n_full_scores, params.top_k)
+        with self._lock:
+            lay = self._ws.get(key)
+            if lay is None:
+                lay = self.layout(B, Q, params)
+                if len(self._ws) > 64:
+                    self._ws.clear()
+                self._ws[key] = lay
+            need = int(lay.total_bytes)
+            if self._buf is None or self._buf.numel() < need:
+                self._buf = None
+                self._buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+            return self._buf, lay
+
+    def max_queries_per_call(self, Q: int, params: FpbParams, budget_bytes: int = 6 << 30) -> int:
+        one = self.layout(1, Q, params).total_bytes
+        two = self.layout(2, Q, params).total_bytes
+        per_q = max(1, two - one)
+        return max(1, int((budget_bytes - one) // per_q) + 1)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # -- search --------------------------------------------------------------------------
+    def search(
+        self, queries: torch.Tensor, params: FpbParams
+    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """queries: fp16 [B, Q, D] on this device.  Returns device tensors
+        (ids int64 [B, top_k], scores f32 [B, top_k], counts int32 [B]).  Asynchronous."""
+        if queries.dim() != 3:
+            raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries.shape)}")
+        if queries.dtype != torch.float16 or queries.device != self.device:
+            raise ValueError("DeviceIndex.search expects fp16 queries on the index device")
+        queries = queries.contiguous()
+        B, Q, D = queries.shape
+        if D != self.dim:
+            raise ValueError(f"query dim {D} != index dim {self.dim}")
+        k = params.top_k
+        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        if B == 0:
+            return ids, scores, counts
+        step = self.max_queries_per_call(Q, params)
+        with torch.cuda.device(self.device):
+            for s in range(0, B, step):
+                e = min(B, s + step)
+                buf, lay = self.workspace(e - s, Q, params)
+                _check(
+                    self._lib.fpb_search_batch(
+                        self._handle, queries[s:e].data_ptr(), e - s, Q, ctypes.byref(params), buf.data_ptr(),
+                        buf.numel(), ids[s:e].data_ptr(), scores[s:e].data_ptr(), counts[s:e].data_ptr(),
+                        self._stream(),
+                    )
+                )
+        return ids, scores, counts
+
+    def search_host(
+        self, queries_host: torch.Tensor, params: FpbParams
+    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """queries_host: fp16 [B, Q, D] in (preferably pinned) HOST memory.  The H2D copy, the
+        search and the D2H copies of the results all happen inside the C-ABI call, which
+        synchronises the stream.  Returns HOST tensors (ids, scores, counts)."""
+        if queries_host.dim() != 3:
+            raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries_host.shape)}")
+        if queries_host.dtype != torch.float16 or queries_host.device.type != "cpu":
+            raise ValueError("search_host expects fp16 queries in host memory")
+        queries_host = queries_host.contiguous()
+        B, Q, D = queries_host.shape
+        if D != self.dim:
+            raise ValueError(f"query dim {D} != index dim {self.dim}")
+        k = params.top_k
+        key = (B, Q, k)
+        with self._lock:
+            io = self._io.get(key)
+            if io is None:
+                self._io.clear()
+                io = {
+                    "d_q": torch.empty((B, Q, D), dtype=torch.float16, device=self.device),
+                    "d_ids": torch.empty((B, k), dtype=torch.int64, device=self.device),
+                    "d_scores": torch.empty((B, k), dtype=torch.float32, device=self.device),
+                    "d_counts": torch.empty((B,), dtype=torch.int32, device=self.device),
+                    "h_ids": torch.empty((B, k), dtype=torch.int64).pin_memory(),
+                    "h_scores": torch.empty((B, k), dtype=torch.float32).pin_memory(),
+                    "h_counts": torch.empty((B,), dtype=torch.int32).pin_memory(),
+                }
+                self._io[key] = io
+        if B == 0:
+            return io["h_ids"], io["h_scores"], io["h_counts"]
+        step = self.max_queries_per_call(Q, params)
+        with torch.cuda.device(self.device):
+            for s in range(0, B, step):
+                e = min(B, s + step)
+                buf, lay = self.workspace(e - s, Q, params)
+                _check(
+                    self._lib.fpb_search_batch_host(
+                        self._handle, queries_host[s:e].data_ptr(), e - s, Q, ctypes.byref(params),
+                        buf.data_ptr(), buf.numel(), io["d_q"][s:e].data_ptr(), io["d_ids"][s:e].data_ptr(),
+                        io["d_scores"][s:e].data_ptr(), io["d_counts"][s:e].data_ptr(),
+                        io["h_ids"][s:e].data_ptr(), io["h_scores"][s:e].data_ptr(),
+                        io["h_counts"][s:e].data_ptr(), self._stream(),
+                    )
+                )
+        return io["h_ids"], io["h_scores"], io["h_counts"]
+
+    def search_records(self, queries: torch.Tensor, params: FpbParams) -> torch.Tensor:
+        """Sharded mode, local half: returns uint8 [B, R, 16] records (approx f32, exact f32,
+        global doc id i64) for this shard's n_full_scores/4 best candidates per query."""
+        queries = queries.contiguous()
+        B, Q, _ = queries.shape
+        buf, lay = self.workspace(B, Q, params)
+        rec = torch.empty((B, lay.R, 16), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(
+                self._lib.fpb_search_shard(
+                    self._handle, queries.data_ptr(), B, Q, ctypes.byref(params), buf.data_ptr(), buf.numel(),
+                    rec.data_ptr(), self._stream(),
+                )
+            )
+        return rec
+
+    def merge_records(
+        self, all_records: torch.Tensor, top_k: int
+    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """all_records: uint8 [n_shards, B, R, 16] (all-gathered).  Global prune + rank."""
+        n_shards, B, R, _ = all_records.shape
+        ids = torch.empty((B, top_k), dtype=torch.int64, device=self.device)
+        scores = torch.empty((B, top_k), dtype=torch.float32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(
+                self._lib.fpb_merge_shards(
+                    all_records.contiguous().data_ptr(), n_shards, B, R, top_k, ids.data_ptr(),
+                    scores.data_ptr(), counts.data_ptr(), self._stream(),
+                )
+            )
+        return ids, scores, counts
+
+    # -- stage-level access for the parity tests and the roofline bench -------------------
+    def run_stages(self, queries: torch.Tensor, params: FpbParams, upto: str = "rank") -> dict[str, Any]:
+        """Run the pipeline stage by stage and return views of every intermediate."""
+        order = ["centroid_scores", "probe", "candidates", "approx", "select", "maxsim", "rank"]
+        queries = queries.contiguous()
+        B, Q, _ = queries.shape
+        buf, lay = self.workspace(B, Q, params)
+        st = self._stream()
+        p = ctypes.byref(params)
+        out: dict[str, Any] = {"layout": lay, "workspace": buf}
+        with torch.cuda.device(self.device):
+            for name in order:
+                if name == "centroid_scores":
+                    _check(self._lib.fpb_stage_centroid_scores(self._handle, queries.data_ptr(), B, Q, p,
+                                                               buf.data_ptr(), buf.numel(), st))
+                elif name == "rank":
+                    k = params.top_k
+                    ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+                    scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+                    counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+                    _check(self._lib.fpb_stage_rank(self._handle, B, Q, p, buf.data_ptr(), buf.numel(),
+                                                    ids.data_ptr(), scores.data_ptr(), counts.data_ptr(), st))
+                    out.update(ids=ids, scores=scores, counts=counts)
+                else:
+                    fn = getattr(self._lib, f"fpb_stage_{name}")
+                    _check(fn(self._handle, B, Q, p, buf.data_ptr(), buf.numel(), st))
+                if name == upto:
+                    break
+        out.update(self.views(buf, lay))
+        return out
+
+    def stage_fn(self, name: str, queries: torch.Tensor, params: FpbParams):
+        """A zero-argument callable that launches one stage on the cached workspace (bench)."""
+        queries = queries.contiguous()
+        B, Q, _ = queries.shape
+        buf, lay = self.workspace(B, Q, params)
+        p = ctypes.byref(params)
+        st = self._stream()
+        if name == "centroid_scores":
+            return lambda: _check(self._lib.fpb_stage_centroid_scores(
+                self._handle, queries.data_ptr(), B, Q, p, buf.data_ptr(), buf.numel(), st))
+        fn = getattr(self._lib, f"fpb_stage_{name}")
+        return lambda: _check(fn(self._handle, B, Q, p, buf.data_ptr(), buf.numel(), st))
+
+    def views(self, buf: torch.Tensor, lay: FpbLayout) -> dict[str, torch.Tensor]:
+        B, Q, Qp, R = lay.B, lay.Q, lay.Qp, lay.R
+        K = self.num_centroids
+
+        def v(off: int, nbytes: int, dtype: torch.dtype, shape: tuple) -> torch.Tensor:
+            return buf[off : off + nbytes].view(dtype).view(*shape)
+
+        return {
+            "S": v(lay.off_S, B * K * Qp * 2, torch.float16, (B, K, Qp)),
+            "tmax": v(lay.off_tmax, B * Qp * lay.n_tiles * 2, torch.float16, (B, Qp, lay.n_tiles)),
+            "cells": v(lay.off_cells, B * Q * lay.n_probe * 4, torch.int32, (B, Q, lay.n_probe)),
+            "n_cand": v(lay.off_n_cand, B * 4, torch.int32, (B,)),
+            "cand": v(lay.off_cand, B * lay.cand_cap * 4, torch.int32, (B, lay.cand_cap)),
+            "approx": v(lay.off_approx, B * lay.cand_cap * 4, torch.float32, (B, lay.cand_cap)),
+            "n_rerank": v(lay.off_n_rerank, B * 4, torch.int32, (B,)),
+            "rerank": v(lay.off_rerank, B * R * 4, torch.int32, (B, R)),
+            "rerank_approx": v(lay.off_rerank_approx, B * R * 4, torch.float32, (B, R)),
+            "exact": v(lay.off_exact, B * R * 4, torch.float32, (B, R)),
+        }
+
+    # -- by-products -----------------------------------------------------------------------
+    def reconstruct(self, doc_ids: list[int]) -> list[torch.Tensor]:
+        """reconstruct_embeddings (rust/utils/embeddings.rs:12-69): fp16 [len, D] per doc."""
+        if not doc_ids:
+            return []
+        ids = torch.tensor(doc_ids, dtype=torch.int64)
+        if int(ids.min()) < 0 or int(ids.max()) >= self.num_documents:
+            raise ValueError("document id out of range")
+        offs = self.doc_offsets.cpu()
+        lens = offs[ids + 1] - offs[ids]
+        out_off = torch.zeros(len(doc_ids) + 1, dtype=torch.int64)
+        out_off[1:] = lens.cumsum(0)
+        total = int(out_off[-1])
+        out = torch.empty((max(total, 1), self.dim), dtype=torch.float16, device=self.device)
+        d_ids = ids.to(self.device, torch.int32)
+        d_off = out_off.to(self.device)
+        with torch.cuda.device(self.device):
+            _check(self._lib.fpb_reconstruct(self._handle, d_ids.data_ptr(), len(doc_ids), d_off.data_ptr(),
+                                             out.data_ptr(), self._stream()))
+        return [out[int(out_off[i]) : int(out_off[i + 1])] for i in range(len(doc_ids))]
+
+    def token_scores(self, queries: torch.Tensor, query_of: torch.Tensor, doc_ids: torch.Tensor) -> torch.Tensor:
+        """fp16 [n, max_len, Q] token matrices for explicit (query, local doc) pairs."""
+        queries = queries.contiguous()
+        n = int(doc_ids.shape[0])
+        Q = int(queries.shape[1])
+        out = torch.zeros((max(n, 1), max(self.max_doc_len, 1), Q), dtype=torch.float16, device=self.device)
+        if n == 0:
+            return out[:0]
+        qo = query_of.to(self.device, torch.int32).contiguous()
+        di = doc_ids.to(self.device, torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _check(self._lib.fpb_token_scores(self._handle, queries.data_ptr(), Q, qo.data_ptr(), di.data_ptr(), n,
+                                              max(self.max_doc_len, 1), out.data_ptr(), self._stream()))
+        return out

@@ -1,0 +1,530 @@
+"""The FastPlaid Python surface on top of the B200 engine.
+
+Same class, method names, argument meaning and error behaviour as the reference's
+``fast_plaid.search.FastPlaid`` (python/fast_plaid/search/fast_plaid.py:325-1186), same index
+directory on disk, PyTorch tensors in and ``list[list[(doc_id, score)]]`` out.  What differs
+is underneath: the whole query batch goes through one C-ABI call into hand-written sm_100a
+kernels (``fast_plaid_b200/csrc``) instead of a per-query loop of ATen ops, and with several
+GPUs the index is sharded by document (one process per GPU, NCCL all-gather of per-shard
+records) instead of replicated.
+
+There is no CPU search path: ``device="cpu"`` can build / update / delete an index directory
+(host-side work) but ``search`` raises.
+"""
+
+from __future__ import annotations
+
+import gc
+import glob
+import json
+import math
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+
+try:  # same dependency as the reference (fast_plaid.py:20-21)
+    from filelock import FileLock
+    from filelock import Timeout as FileLockTimeout
+except ImportError:  # pragma: no cover - filelock ships with the image
+    FileLock = None  # type: ignore
+    FileLockTimeout = Exception  # type: ignore
+
+from .. import engine as _engine
+from ..engine import DeviceIndex, IndexTensors
+from ..index import build as _build
+from ..index import store as _store
+
+
+class _NullLock:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def acquire(self, timeout: float = -1):
+        return self
+
+    def release(self):
+        pass
+
+
+def save_list_tensors_on_disk(path: str, tensors: list[torch.Tensor]) -> None:
+    """Pickled object array of raw document tensors (load.py:430-444)."""
+    arr = np.empty(len(tensors), dtype=object)
+    for i, t in enumerate(tensors):
+        arr[i] = t.cpu().numpy()
+    np.save(path, arr, allow_pickle=True)
+
+
+def _results_to_lists(ids: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor) -> list[list[tuple[int, float]]]:
+    """Re-zip of search_on_device (fast_plaid.py:247-253)."""
+    ids_l = ids.tolist()
+    sc_l = scores.tolist()
+    out = []
+    for b, n in enumerate(counts.tolist()):
+        out.append(list(zip(ids_l[b][:n], sc_l[b][:n])))
+    return out
+
+
+class FastPlaid:
+    """Create, update and search a PLAID index; drop-in for the reference class."""
+
+    def __init__(
+        self,
+        index: str,
+        device: str | list[str] | None = None,
+        low_memory: bool = True,
+        shard: tuple[int, int] | str | None = None,
+        **kwargs: Any,  # noqa: ARG002
+    ) -> None:
+        """``index``/``device``/``low_memory`` as in the reference (fast_plaid.py:328-385).
+
+        ``low_memory`` is accepted and ignored: a B200 holds the whole index in HBM.
+        ``shard``: ``(rank, world)`` makes this process own one contiguous document range and
+        merge with the other ranks through ``torch.distributed`` (NCCL); ``"auto"`` takes
+        rank/world from an initialised process group.
+        """
+        if device is not None and isinstance(device, str):
+            self.devices = [device]
+        elif isinstance(device, list):
+            self.devices = device
+        elif torch.cuda.is_available():
+            self.devices = [f"cuda:{i}" for i in range(torch.cuda.device_count())]
+        else:
+            self.devices = ["cpu"]
+        self.devices = ["cuda:0" if d == "cuda" else d for d in self.devices]
+        self.devices = list(dict.fromkeys(self.devices))
+        for d in self.devices:
+            if d != "cpu" and not (d.startswith("cuda:") and d[5:].isdigit()):
+                raise ValueError(f"Unsupported device string: '{d}'")  # load.rs:16-37
+
+        self.index = index
+        self.low_memory = low_memory
+        if shard == "auto":
+            import torch.distributed as dist
+
+            shard = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else None
+        self.shard: tuple[int, int] | None = shard  # type: ignore[assignment]
+        if self.shard is not None and len(self.devices) != 1:
+            raise ValueError("sharded mode is one process per GPU: pass exactly one device")
+
+        if not os.path.exists(self.index):
+            os.makedirs(self.index, exist_ok=True)
+        self.lock_path = os.path.join(self.index, "plaid.lock")
+        self.lock = FileLock(self.lock_path) if FileLock is not None else _NullLock()
+        self._last_known_mtime = 0.0
+        self._index_swap_lock = threading.Lock()
+        self.indices: dict[str, DeviceIndex | None] = {}
+        self._check_and_reload_index()
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        with self._index_swap_lock:
+            for idx in self.indices.values():
+                if idx is not None:
+                    idx.close()
+            self.indices.clear()
+        gc.collect()
+
+    def __enter__(self) -> "FastPlaid":
+        return self
+
+    def __exit__(self, exc_type, exc_val, exc_tb) -> None:
+        self.close()
+
+    # ------------------------------------------------------------------ (re)loading
+    def _update_mtime(self) -> None:
+        meta_path = os.path.join(self.index, "metadata.json")
+        if os.path.exists(meta_path):
+            self._last_known_mtime = Path(meta_path).stat().st_mtime
+
+    def _load_all(self) -> dict[str, DeviceIndex | None]:
+        """disk -> CPU tensors -> one DeviceIndex per CUDA device (load.py:368-427)."""
+        new: dict[str, DeviceIndex | None] = {d: None for d in self.devices}
+        if not os.path.exists(os.path.join(self.index, "metadata.json")):
+            return new
+        try:
+            data = _store.read_index(self.index)
+        except Exception as e:  # load.py:393-399
+            print(f"Critical Error loading index from disk: {e}")
+            return new
+        if data is None:
+            return new
+        self._host_data = data if any(d == "cpu" for d in self.devices) else None
+        base = 0
+        if self.shard is not None:
+            data, base = _engine.shard_tensors(data, self.shard[0], self.shard[1])
+
+        def provision(device: str):
+            if device == "cpu":
+                return device, None
+            try:
+                return device, DeviceIndex(data, device, doc_id_base=base)
+            except Exception as e:  # load.py:414-416
+                print(f"Warning: Failed to load index on {device}: {e}")
+                return device, None
+
+        if len(self.devices) == 1:
+            dev, idx = provision(self.devices[0])
+            new[dev] = idx
+        else:
+            with ThreadPoolExecutor(max_workers=len(self.devices)) as ex:
+                new = dict(ex.map(provision, self.devices))
+        return new
+
+    def _check_and_reload_index(self, blocking: bool = True) -> bool:
+        """Optimistic mtime check + double-checked reload under the file lock
+        (fast_plaid.py:433-514)."""
+        meta_path = os.path.join(self.index, "metadata.json")
+        if not os.path.exists(meta_path):
+            with self._index_swap_lock:
+                for d in self.devices:
+                    self.indices[d] = None
+            return True
+        current = Path(meta_path).stat().st_mtime
+        if current <= self._last_known_mtime and self._loaded():
+            return True
+        if not blocking:
+            try:
+                self.lock.acquire(timeout=0)
+            except FileLockTimeout:
+                return False
+            try:
+                return self._reload_under_lock()
+            finally:
+                self.lock.release()
+        with self.lock:
+            return self._reload_under_lock()
+
+    def _loaded(self) -> bool:
+        return any(v is not None for v in self.indices.values()) or (
+            self.devices == ["cpu"] and getattr(self, "_cpu_loaded", False)
+        )
+
+    def _reload_under_lock(self) -> bool:
+        meta_path = os.path.join(self.index, "metadata.json")
+        current = Path(meta_path).stat().st_mtime
+        if current <= self._last_known_mtime and self._loaded():
+            return True
+        new = self._load_all()
+        with self._index_swap_lock:
+            old = self.indices
+            self.indices = new
+            self._last_known_mtime = current
+            self._cpu_loaded = True
+        for idx in old.values():
+            if idx is not None:
+                idx.close()
+        return True
+
+    def _swap_in_fresh(self) -> None:
+        new = self._load_all()
+        with self._index_swap_lock:
+            old = self.indices
+            self.indices = new
+            self._update_mtime()
+            self._cpu_loaded = True
+        for idx in old.values():
+            if idx is not None:
+                idx.close()
+
+    # ------------------------------------------------------------------ create / update / delete
+    def _format_embeddings(self, embeddings):
+        if isinstance(embeddings, torch.Tensor):
+            return embeddings.squeeze(0) if embeddings.dim() == 3 and embeddings.shape[0] == 1 else embeddings
+        return [e.squeeze(0) if e.dim() == 3 else e for e in embeddings]
+
+    @staticmethod
+    def _prepare_index_directory(index_path: str) -> None:
+        """fast_plaid.py:715-741"""
+        if os.path.isdir(index_path):
+            for pat in ("*.json", "*.npy"):
+                for f in glob.glob(os.path.join(index_path, pat)):
+                    try:
+                        os.remove(f)
+                    except OSError:
+                        pass
+        elif not os.path.exists(index_path):
+            os.makedirs(index_path)
+
+    @torch.inference_mode()
+    def create(
+        self,
+        documents_embeddings: list[torch.Tensor] | torch.Tensor,
+        kmeans_niters: int = 4,
+        max_points_per_centroid: int = 256,
+        nbits: int = 4,
+        n_samples_kmeans: int | None = None,
+        batch_size: int = 25_000,
+        seed: int = 42,
+        use_triton_kmeans: bool | None = None,  # noqa: ARG002  (no Triton in this build)
+        metadata: list[dict[str, Any]] | None = None,
+        start_from_scratch: int = 1000,
+        compress_only: bool = False,
+    ) -> "FastPlaid":
+        """Create and save the index (fast_plaid.py:516-637)."""
+        with self.lock:
+            docs = self._format_embeddings(documents_embeddings)
+            if isinstance(docs, torch.Tensor):
+                docs = list(docs) if docs.dim() == 3 else [docs]
+            num_docs = len(docs)
+            self._prepare_index_directory(self.index)
+            if metadata is not None:
+                if len(metadata) != num_docs:
+                    raise ValueError(
+                        f"The length of metadata ({len(metadata)}) must match the number of "
+                        f"documents_embeddings ({num_docs})."
+                    )
+                from ..filtering import create as _meta_create
+
+                _meta_create(index=self.index, metadata=metadata)
+            if num_docs <= start_from_scratch:
+                save_list_tensors_on_disk(os.path.join(self.index, "embeddings.npy"), docs)
+            dim = int(docs[0].shape[-1])
+            primary = self.devices[0]
+            centroids = _build.compute_kmeans(
+                docs, dim, primary, kmeans_niters, max_points_per_centroid, seed, n_samples_kmeans
+            )
+            _build.create_index(docs, self.index, centroids, nbits=nbits, batch_size=batch_size, seed=seed,
+                                compress_only=compress_only, device=primary)
+            del centroids
+            gc.collect()
+            self._swap_in_fresh()
+        return self
+
+    @torch.inference_mode()
+    def update(
+        self,
+        documents_embeddings: list[torch.Tensor] | torch.Tensor,
+        metadata: list[dict[str, Any]] | None = None,
+        batch_size: int = 25_000,
+        kmeans_niters: int = 4,
+        max_points_per_centroid: int = 256,
+        n_samples_kmeans: int | None = None,
+        seed: int = 42,
+        start_from_scratch: int = 999,
+        buffer_size: int = 100,  # noqa: ARG002
+        use_triton_kmeans: bool | None = False,  # noqa: ARG002
+    ) -> "FastPlaid":
+        """Add documents (fast_plaid.py:640-713, update.py:206-452).
+
+        Kept behaviour: create-if-missing; while the index holds at most ``start_from_scratch``
+        documents it is rebuilt from the raw ``embeddings.npy`` plus the new documents;
+        afterwards new documents are encoded with the existing codec and appended.  The
+        reference's centroid-expansion buffer (update.py:65-203) is an index-mutation policy
+        outside the search hot path and is not reproduced: appended documents always use the
+        existing centroids.
+        """
+        from ..index import update as _update
+
+        with self.lock:
+            docs = self._format_embeddings(documents_embeddings)
+            if isinstance(docs, torch.Tensor):
+                docs = list(docs) if docs.dim() == 3 else [docs]
+            _update.process_update(self, docs, metadata, batch_size, kmeans_niters, max_points_per_centroid,
+                                   n_samples_kmeans, seed, start_from_scratch)
+            self._swap_in_fresh()
+        return self
+
+    @torch.inference_mode()
+    def delete(self, subset: list[int], _delete_metadata: bool = True, _delete_buffer: bool = True) -> "FastPlaid":  # noqa: ARG002
+        """Remove documents and renumber the rest (fast_plaid.py:1045-1157, delete.rs:26-145)."""
+        from ..index import update as _update
+
+        with self.lock:
+            _update.delete_from_index(self.index, subset, device=self.devices[0])
+            if os.path.exists(os.path.join(self.index, "metadata.db")) and _delete_metadata:
+                from ..filtering import delete as _meta_delete
+
+                _meta_delete(index=self.index, subset=subset)
+            emb_path = os.path.join(self.index, "embeddings.npy")
+            if os.path.exists(emb_path):
+                arr = np.load(emb_path, allow_pickle=True)
+                drop = {i for i in subset if i < len(arr)}
+                if drop:
+                    keep = [torch.from_numpy(arr[i]) for i in range(len(arr)) if i not in drop]
+                    if keep:
+                        save_list_tensors_on_disk(emb_path, keep)
+                    else:
+                        os.remove(emb_path)
+            self._swap_in_fresh()
+        return self
+
+    # ------------------------------------------------------------------ search
+    def _prepare_search(self, queries_embeddings, subset):
+        """fast_plaid.py:743-795"""
+        self._check_and_reload_index(blocking=False)
+        with self._index_swap_lock:
+            search_indices = dict(self.indices)
+        if any(idx is None for idx in search_indices.values()):
+            self._check_and_reload_index(blocking=True)
+            with self._index_swap_lock:
+                search_indices = dict(self.indices)
+        if not os.path.exists(os.path.join(self.index, "metadata.json")):
+            raise FileNotFoundError(
+                f"Index metadata not found in '{self.index}'. Please create the index before searching."
+            )
+        for device in self.devices:
+            if device == "cpu":
+                raise _engine.EngineUnavailableError(
+                    "fast_plaid_b200 has no CPU search path: open the index with device='cuda:N' "
+                    "(the CPU restatement of the reference lives in oracle/ and is test-only)."
+                )
+            if search_indices.get(device) is None:
+                raise RuntimeError(
+                    f"Index could not be loaded on device '{device}'. Check CUDA memory or device availability."
+                )
+        if isinstance(queries_embeddings, list):
+            queries_embeddings = torch.nn.utils.rnn.pad_sequence(
+                sequences=[e[0] if e.dim() == 3 else e for e in queries_embeddings],
+                batch_first=True,
+                padding_value=0.0,
+            )
+        num_queries = queries_embeddings.shape[0]
+        if subset is not None:
+            if isinstance(subset, int):
+                subset = [subset] * num_queries
+            if isinstance(subset, list) and len(subset) == 0:
+                subset = None
+            if isinstance(subset, list) and isinstance(subset[0], int):
+                subset = [subset] * num_queries
+            if subset is not None and len(subset) != num_queries:
+                raise ValueError("Subset length must match number of queries.")
+        return search_indices, queries_embeddings, subset
+
+    def _search_device(self, idx: DeviceIndex, queries: torch.Tensor, params) -> list[list[tuple[int, float]]]:
+        """search_on_device (fast_plaid.py:188-253) for the whole batch."""
+        if queries.dim() != 3:
+            raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries.shape)}")
+        if self.shard is not None:
+            return self._search_sharded(idx, queries, params)
+        if queries.device.type == "cuda":
+            q16 = queries.to(device=idx.device, dtype=torch.float16)  # fast_plaid.py:241
+            ids, scores, counts = idx.search(q16, params)
+            return _results_to_lists(ids.cpu(), scores.cpu(), counts.cpu())
+        q16 = queries.to(torch.float16)  # cast on the host like the reference (fast_plaid.py:241)
+        if not q16.is_pinned():
+            q16 = q16.contiguous().pin_memory()
+        ids, scores, counts = idx.search_host(q16, params)
+        return _results_to_lists(ids, scores, counts)
+
+    def _search_sharded(self, idx: DeviceIndex, queries: torch.Tensor, params) -> list[list[tuple[int, float]]]:
+        """Document-sharded search: local records -> NCCL all-gather -> global prune + rank."""
+        import torch.distributed as dist
+
+        q16 = queries.to(device=idx.device, dtype=torch.float16, non_blocking=True)
+        rec = idx.search_records(q16, params)
+        world = self.shard[1]
+        gathered = torch.empty((world,) + tuple(rec.shape), dtype=torch.uint8, device=idx.device)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), rec.view(-1))
+        else:
+            gathered.copy_(rec.unsqueeze(0))
+        ids, scores, counts = idx.merge_records(gathered, params.top_k)
+        return _results_to_lists(ids.cpu(), scores.cpu(), counts.cpu())
+
+    @torch.inference_mode()
+    def search(
+        self,
+        queries_embeddings: torch.Tensor | list[torch.Tensor],
+        top_k: int = 10,
+        batch_size: int = 2000,
+        n_full_scores: int = 4096,
+        n_ivf_probe: int = 8,
+        show_progress: bool = True,  # noqa: ARG002  (one launch sequence per batch: nothing to show)
+        subset: list[list[int]] | list[int] | None = None,
+        n_processes: int | None = None,  # noqa: ARG002  (CPU-only knob in the reference)
+    ) -> list[list[tuple[int, float]]]:
+        """Search the index (fast_plaid.py:930-983).  Returns, per query, up to ``top_k``
+        ``(doc_id, score)`` pairs in rank order."""
+        search_indices, queries, subset = self._prepare_search(queries_embeddings, subset)
+        if subset is not None:
+            raise NotImplementedError(
+                "subset= filtering is not wired into the B200 engine yet (SURVEY.md 8f-4)."
+            )
+        params = DeviceIndex.make_params(top_k, n_full_scores, n_ivf_probe, batch_size)
+        if len(self.devices) == 1:
+            return self._search_device(search_indices[self.devices[0]], queries, params)
+        # several devices in ONE process: replicated index, query list split across devices
+        # (the reference's multi-GPU mode, fast_plaid.py:893-928)
+        n = len(self.devices)
+        chunk = math.ceil(queries.shape[0] / n)
+        chunks = list(torch.split(queries, chunk))
+        with ThreadPoolExecutor(max_workers=n) as ex:
+            futs = [
+                ex.submit(self._search_device, search_indices[d], chunks[i], params)
+                for i, d in enumerate(self.devices)
+                if i < len(chunks)
+            ]
+        out: list[list[tuple[int, float]]] = []
+        for f in futs:
+            out.extend(f.result())
+        return out
+
+    @torch.inference_mode()
+    def search_token_scores(
+        self,
+        queries_embeddings: torch.Tensor | list[torch.Tensor],
+        top_k: int = 10,
+        batch_size: int = 2000,
+        n_full_scores: int = 4096,
+        n_ivf_probe: int = 8,
+        show_progress: bool = True,
+        subset: list[list[int]] | list[int] | None = None,
+        n_processes: int | None = None,
+    ) -> list[list[tuple[int, float, torch.Tensor]]]:
+        """``search`` plus, per result, the ``[query_tokens, doc_tokens]`` fp16 similarity
+        matrix (fast_plaid.py:985-1043, search.rs:668-686)."""
+        if self.shard is not None or len(self.devices) != 1:
+            raise NotImplementedError("search_token_scores runs on a single, unsharded device")
+        base = self.search(queries_embeddings, top_k, batch_size, n_full_scores, n_ivf_probe, show_progress,
+                           subset, n_processes)
+        _, queries, _ = self._prepare_search(queries_embeddings, None)
+        idx = self.indices[self.devices[0]]
+        q16 = queries.to(device=idx.device, dtype=torch.float16)
+        pairs_q, pairs_d = [], []
+        for b, res in enumerate(base):
+            for doc_id, _ in res:
+                pairs_q.append(b)
+                pairs_d.append(doc_id)
+        mats = idx.token_scores(q16, torch.tensor(pairs_q, dtype=torch.int32), torch.tensor(pairs_d, dtype=torch.int32))
+        lens = (idx.doc_offsets[1:] - idx.doc_offsets[:-1]).cpu()
+        out, k = [], 0
+        for res in base:
+            row = []
+            for doc_id, score in res:
+                n = int(lens[doc_id])
+                row.append((doc_id, score, mats[k, :n, :].transpose(0, 1).contiguous().cpu()))
+                k += 1
+            out.append(row)
+        return out
+
+    @torch.inference_mode()
+    def get_embeddings(self, subset: list[int]) -> list[torch.Tensor]:
+        """Decompressed, normalised fp16 embeddings of the given documents
+        (fast_plaid.py:1159-1186, embeddings.rs:12-69)."""
+        self._check_and_reload_index(blocking=False)
+        if not subset:
+            return []
+        with self._index_swap_lock:
+            idx = self.indices.get(self.devices[0])
+        if idx is None:
+            raise _engine.EngineUnavailableError("get_embeddings needs the index loaded on a CUDA device")
+        return [t.cpu() for t in idx.reconstruct(list(subset))]
+
+    # ------------------------------------------------------------------ in-memory construction
+    @classmethod
+    def from_tensors(cls, data: IndexTensors, device: str, doc_id_base: int = 0) -> DeviceIndex:
+        """Bench / test helper: put already-built index tensors straight into HBM."""
+        return DeviceIndex(data, device, doc_id_base=doc_id_base)
+
+
+def read_num_documents(index_path: str) -> int:
+    with open(os.path.join(index_path, "metadata.json")) as f:
+        return int(json.load(f).get("num_documents", 0))

@@ -1,0 +1,178 @@
+/*
+ * fastplaid_b200.h -- C ABI of the B200-native PLAID search engine.
+ *
+ * This is the drop-in boundary for the search hot path of lightonai/fast-plaid
+ * (v1.4.6 @ 87f96f6).  In the reference that path sits behind the PyO3 module
+ * `fast_plaid.fast_plaid_rust` (rust/lib.rs:366-383).  Each entry point below names the
+ * reference interface it replaces.  Conventions:
+ *
+ *   - plain C types only; every pointer named `d_*` is a DEVICE pointer on the index's
+ *     GPU, every pointer named `h_*` is a HOST pointer, `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success or a negative code; the message is available
+ *     from fpb_last_error() (thread-local).  No exception crosses the boundary.  The
+ *     reference's PyValueError / PyRuntimeError (rust/utils/errors.rs:5-7) are raised by
+ *     the Python host from these codes;
+ *   - all entry points are asynchronous w.r.t. the host on `stream` unless their name
+ *     ends in `_host` (those synchronise the stream before returning);
+ *   - an fpb_index is immutable after creation and may be searched concurrently from
+ *     several host threads on different streams with different workspaces, like the
+ *     reference's `LoadedIndex` (`unsafe impl Send/Sync`, rust/search/load.rs:58-59).
+ *     It does NOT own the big arrays: the caller (PyTorch) keeps them alive.
+ */
+#ifndef FASTPLAID_B200_H_
+#define FASTPLAID_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPB_OK 0
+#define FPB_ERR_INVALID (-1)  /* bad argument -> Python ValueError  (errors.rs:5-7)   */
+#define FPB_ERR_CUDA (-2)     /* CUDA runtime failure -> RuntimeError                  */
+#define FPB_ERR_UNSUPPORTED (-3)
+#define FPB_ERR_WORKSPACE (-4) /* workspace too small                                  */
+#define FPB_ERR_NO_IVF (-5)   /* compress_only index: search refused (search.rs:227-232) */
+
+typedef struct fpb_index fpb_index;
+
+/* Thread-local message of the last failing call in this thread. */
+const char* fpb_last_error(void);
+/* ABI version (bumped on any signature change). */
+int fpb_abi_version(void);
+
+/*
+ * fpb_index_create  -- replaces `construct_index` (rust/search/load.rs:122-186) and
+ * `ResidualCodec::load` (rust/utils/residual_codec.rs:72-152).
+ *
+ *   d_centroids       f16 [n_centroids, dim], row-major            (load.rs:145)
+ *   d_bucket_weights  f16 [1 << nbits]                              (load.rs:150)
+ *   d_doc_offsets     i64 [n_docs + 1], exclusive cumsum of doclens (tensor.rs:221-224)
+ *   d_doc_codes       i32 [n_tokens]   (narrowed from the on-disk int64 by the loader)
+ *   d_doc_residuals   u8  [n_tokens, dim*nbits/8]
+ *   d_ivf_offsets     i64 [n_centroids + 1]  or NULL for a compress_only index
+ *   d_ivf_pids        i32 [n_ivf]            (LOCAL doc ids, ascending within a list)
+ *   doc_id_base       global id of local doc 0 (document sharding; 0 on one GPU)
+ *
+ * The two 256-entry LUTs of the reference collapse into one (1<<nbits)-entry permuted
+ * weight table w_perm[i] = bucket_weights[bitrev_nbits(i)] built here on the host.
+ */
+int fpb_index_create(fpb_index** out, int device, int nbits, int dim, int64_t n_centroids,
+                     const void* d_centroids, const void* d_bucket_weights, int64_t n_docs,
+                     const int64_t* d_doc_offsets, const int32_t* d_doc_codes,
+                     const uint8_t* d_doc_residuals, const int64_t* d_ivf_offsets,
+                     const int32_t* d_ivf_pids, int64_t n_ivf, int64_t max_doc_len,
+                     int64_t doc_id_base);
+void fpb_index_destroy(fpb_index* index);
+
+/* Search parameters -- mirrors `SearchParameters` (rust/search/search.rs:171-200).
+ * `batch_size` (document batch of the approximate stage) only bounds memory in the
+ * reference and does not change values (search.rs:558-586); it is accepted and ignored. */
+typedef struct fpb_params {
+  int32_t n_ivf_probe;   /* search.rs:185, default 8    */
+  int32_t n_full_scores; /* search.rs:179, default 4096 */
+  int32_t top_k;         /* search.rs:182               */
+  int32_t batch_size;    /* search.rs:176, ignored      */
+} fpb_params;
+
+/* Byte offsets of every intermediate inside the workspace, so the parity tests can read
+ * each stage (S, probed cells, candidates, approx scores, rerank list, exact scores)
+ * exactly as the oracle dumps them.  All offsets are multiples of 256. */
+typedef struct fpb_layout {
+  int64_t total_bytes;
+  int32_t B, Q, Qp, n_tiles, R, n_probe, cand_cap, bitmap_words;
+  int64_t off_queries;   /* f16 [B, Qp, D]  zero-padded queries                       */
+  int64_t off_S;         /* f16 [B, K, Qp]  centroid scores          (search.rs:491)  */
+  int64_t off_tmax;      /* f16 [B, Qp, n_tiles] per-128-centroid-tile column maxima  */
+  int64_t off_cells;     /* i32 [B, Q, n_probe]  probed cells        (search.rs:520-528) */
+  int64_t off_bitmap;    /* u32 [B, bitmap_words]                                     */
+  int64_t off_n_cand;    /* i32 [B]                                                   */
+  int64_t off_cand;      /* i32 [B, cand_cap] sorted unique doc ids  (search.rs:535-541) */
+  int64_t off_approx;    /* f32 [B, cand_cap]                        (search.rs:554-592) */
+  int64_t off_work;      /* i32 [B + 8] chunk prefix + counters                       */
+  int64_t off_n_rerank;  /* i32 [B]                                                   */
+  int64_t off_rerank;    /* i32 [B, R] doc ids, (approx desc, id asc) (search.rs:602-619) */
+  int64_t off_rerank_approx; /* f32 [B, R]                                            */
+  int64_t off_exact;     /* f32 [B, R]                               (search.rs:651-656) */
+} fpb_layout;
+
+/* Workspace sizing for a batch of B queries of Q tokens. */
+int fpb_workspace_layout(const fpb_index* index, int B, int Q, const fpb_params* params,
+                         fpb_layout* out);
+
+/*
+ * fpb_search_batch -- replaces `pysearch` -> `search_many` -> `search`
+ * (rust/lib.rs:195-223, rust/search/search.rs:219-288, :471-696) for a whole batch.
+ *
+ *   d_queries     f16 [B, Q, dim]  (already cast to fp16, fast_plaid.py:241)
+ *   d_out_ids     i64 [B, top_k]   global doc ids, rank order
+ *   d_out_scores  f32 [B, top_k]
+ *   d_out_counts  i32 [B]          min(top_k, #reranked)  (search.rs:666)
+ * Unused tail entries are id -1 / score -inf.
+ */
+int fpb_search_batch(const fpb_index* index, const void* d_queries, int B, int Q,
+                     const fpb_params* params, void* d_workspace, size_t workspace_bytes,
+                     int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts,
+                     void* stream);
+
+/* Same call with HOST buffers: H2D of the queries, the search, D2H of the results and a
+ * stream synchronise all happen inside.  d_out_* are device scratch of the same shapes. */
+int fpb_search_batch_host(const fpb_index* index, const void* h_queries, int B, int Q,
+                          const fpb_params* params, void* d_workspace, size_t workspace_bytes,
+                          void* d_queries_staging, int64_t* d_out_ids, float* d_out_scores,
+                          int32_t* d_out_counts, int64_t* h_out_ids, float* h_out_scores,
+                          int32_t* h_out_counts, void* stream);
+
+/* ---- stage-level entry points (parity tests, roofline bench).  Each runs one stage of
+ * search.rs on the workspace laid out by fpb_workspace_layout. ---- */
+int fpb_stage_centroid_scores(const fpb_index*, const void* d_queries, int B, int Q,
+                              const fpb_params*, void* d_workspace, size_t, void* stream); /* search.rs:491 */
+int fpb_stage_probe(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,
+                    size_t, void* stream); /* search.rs:520-532 */
+int fpb_stage_candidates(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,
+                         size_t, void* stream); /* search.rs:535-541 */
+int fpb_stage_approx(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,
+                     size_t, void* stream); /* search.rs:554-592 */
+int fpb_stage_select(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,
+                     size_t, void* stream); /* search.rs:602-619 */
+int fpb_stage_maxsim(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,
+                     size_t, void* stream); /* search.rs:626-656 (+ decompress :53-107) */
+int fpb_stage_rank(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,
+                   size_t, int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts,
+                   void* stream); /* search.rs:659-666 */
+
+/* ---- document-sharded search (new; the reference replicates the index and splits the
+ * query list, fast_plaid.py:893-928).  Each rank runs fpb_search_shard on its shard and
+ * emits R fixed-size records per query; the host all-gathers them (NCCL) and every rank
+ * runs fpb_merge_shards, which re-applies the reference's GLOBAL pruning rule
+ * (top n_full_scores/4 by approximate score, search.rs:605-619) before the final sort. */
+typedef struct fpb_record {
+  float approx;   /* -inf for padding */
+  float exact;
+  int64_t doc_id; /* global id, -1 for padding */
+} fpb_record;
+
+int fpb_search_shard(const fpb_index* index, const void* d_queries, int B, int Q,
+                     const fpb_params* params, void* d_workspace, size_t workspace_bytes,
+                     fpb_record* d_records /* [B, R] */, void* stream);
+int fpb_merge_shards(const fpb_record* d_all_records /* [n_shards, B, R] */, int n_shards,
+                     int B, int R, int top_k, int64_t* d_out_ids, float* d_out_scores,
+                     int32_t* d_out_counts, void* stream);
+
+/* ---- by-products of the MaxSim kernel ("next" rows of SURVEY.md 8f-3) ---- */
+/* reconstruct_embeddings (rust/utils/embeddings.rs:12-69): decompressed, normalised
+ * fp16 rows of the given local docs, concatenated.  d_out: f16 [sum(len), dim]. */
+int fpb_reconstruct(const fpb_index* index, const int32_t* d_doc_ids, int n, const int64_t* d_out_offsets,
+                    void* d_out, void* stream);
+/* token matrices of search_many_with_token_scores (search.rs:668-686):
+ * d_out f16 [n, max_len, Q] row t = doc token, col = query token, for n (query, doc) pairs. */
+int fpb_token_scores(const fpb_index* index, const void* d_queries, int Q, const int32_t* d_query_of,
+                     const int32_t* d_doc_ids, int n, int64_t max_len, void* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTPLAID_B200_H_ */

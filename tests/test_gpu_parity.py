@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle.
+
+What is bit-exact and what is toleranced (DESIGN.md "Parity contract"):
+  * index / integer stages (probe cells, candidate ids, pruning, ranking) are compared
+    exactly, under the canonical tie rule, on the GPU's own fp16 score table S;
+  * the two fp32-accumulated dot products (S and the MaxSim token scores) and the fp32 norm
+    may differ from ATen's CPU kernels by the accumulation order, i.e. by one fp16 ulp on a
+    small fraction of entries -- the tests bound both the size (<= 1 ulp) and the fraction;
+  * final scores: within 1e-3 relative (the tolerance BASELINE.json states).
+"""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+from util import (build_oracle_index, fp16_ulp_diff, make_docs, make_queries, oracle_exact_scores,
+                  ranking_consistent, to_index_tensors)
+
+from oracle import plaid_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    # name: (n_docs, min_len, max_len, dim, nbits, B, Q, top_k, n_full, n_probe, noisy_queries)
+    "base": (1000, 30, 100, 128, 4, 8, 32, 10, 256, 8, True),
+    "cfg1_shape": (400, 300, 300, 128, 4, 10, 50, 10, 4096, 8, False),
+    "ragged_short": (600, 1, 40, 128, 4, 6, 32, 20, 128, 4, True),
+    "nbits2": (500, 20, 80, 128, 2, 4, 32, 10, 256, 8, True),
+    "dim64": (500, 20, 80, 64, 4, 4, 20, 10, 256, 8, True),
+    "probe1": (500, 20, 80, 128, 4, 4, 16, 5, 64, 1, True),
+    "q64": (300, 50, 120, 128, 4, 3, 64, 10, 256, 16, True),
+}
+
+_cache: dict = {}
+
+
+def _setup(name: str, device: str):
+    if name in _cache:
+        return _cache[name]
+    from fast_plaid_b200.engine import DeviceIndex
+
+    n_docs, lo, hi, dim, nbits, B, Q, top_k, n_full, n_probe, noisy = CONFIGS[name]
+    docs = make_docs(n_docs, lo, hi, dim=dim, seed=1234)
+    oidx, _ = build_oracle_index(docs, nbits=nbits)
+    didx = DeviceIndex(to_index_tensors(oidx), device)
+    queries = make_queries(B, Q, dim=dim, seed=4321, docs=docs if noisy else None)
+    params = DeviceIndex.make_params(top_k, n_full, n_probe)
+    q16 = queries.to(torch.float16)
+    stages = didx.run_stages(q16.to(device), params)
+    torch.cuda.synchronize()
+    _cache[name] = (oidx, didx, queries, params, stages)
+    return _cache[name]
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_centroid_scores(name, cuda_device):
+    oidx, didx, queries, params, st = _setup(name, cuda_device)
+    Q = queries.shape[1]
+    S_gpu = st["S"][:, :, :Q].cpu()
+    bad = 0
+    total = 0
+    for b in range(queries.shape[0]):
+        S_ref = oidx.centroids.matmul(queries[b].half().t())  # search.rs:491
+        d = fp16_ulp_diff(S_gpu[b], S_ref)
+        assert int(d.max()) <= 1, f"query {b}: S differs by {int(d.max())} fp16 ulps"
+        bad += int((d > 0).sum())
+        total += d.numel()
+    assert bad / total < 2e-3, f"{bad}/{total} S entries differ by one ulp"
+    # padded query columns are exactly zero
+    if st["S"].shape[2] > Q:
+        assert float(st["S"][:, :, Q:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_integer_stages_bit_exact_given_S(name, cuda_device):
+    """probe cells, candidates, approx scores and the pruned list must equal the canonical
+    oracle exactly when it is fed the GPU's own S."""
+    oidx, didx, queries, params, st = _setup(name, cuda_device)
+    B, Q = queries.shape[0], queries.shape[1]
+    n_inexact = 0
+    for b in range(B):
+        S_b = st["S"][b, :, :Q].cpu().contiguous()
+        ref = po.search_one(queries[b], oidx, params.n_ivf_probe, 2000, params.n_full_scores, params.top_k,
+                            ties="canonical", return_stages=True, inject={"S": S_b})
+        cells_gpu = torch.unique(st["cells"][b].cpu().flatten().long())
+        cells_gpu = cells_gpu[cells_gpu >= 0]
+        assert torch.equal(cells_gpu, ref["cells"]), f"query {b}: probed cells differ"
+        n = int(st["n_cand"][b])
+        cand_gpu = st["cand"][b, :n].cpu().long()
+        assert torch.equal(cand_gpu, ref["candidates"]), f"query {b}: candidate ids differ"
+        approx_gpu = st["approx"][b, :n].cpu()
+        if not torch.equal(approx_gpu, ref["approx"]):
+            # fp32 sums of fp16 values: exact unless a partial sum needs > 24 bits
+            rel = ((approx_gpu - ref["approx"]).abs() / ref["approx"].abs().clamp_min(1.0)).max()
+            assert float(rel) < 1e-6, f"query {b}: approx scores differ by {float(rel)}"
+            n_inexact += 1
+            continue
+        r = int(st["n_rerank"][b])
+        rer_gpu = st["rerank"][b, :r].cpu().long()
+        assert r == ref["rerank"].shape[0]
+        # canonical order of the pruned list is (approx desc, id asc) when pruning happened,
+        # id order otherwise -- compare as the oracle produced it
+        assert torch.equal(rer_gpu, ref["rerank"]), f"query {b}: pruned list differs"
+    assert n_inexact <= B // 2
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_exact_scores(name, cuda_device):
+    oidx, didx, queries, params, st = _setup(name, cuda_device)
+    B, Q = queries.shape[0], queries.shape[1]
+    flips = 0
+    total = 0
+    for b in range(B):
+        r = int(st["n_rerank"][b])
+        rer = st["rerank"][b, :r].cpu().long()
+        if r == 0:
+            continue
+        # oracle exact scores of exactly the documents the GPU re-ranked
+        ref = oracle_exact_scores(oidx, queries[b], rer.tolist())
+        got = st["exact"][b, :r].cpu()
+        rel = (got - ref).abs() / ref.abs().clamp_min(1.0)
+        assert float(rel.max()) < 1e-3, f"query {b}: exact score off by {float(rel.max())} relative"
+        flips += int((got != ref).sum())
+        total += r
+    # fp16-faithful arithmetic: the vast majority of scores are bit-identical
+    assert flips / max(total, 1) < 0.05, f"{flips}/{total} exact scores not bit-identical"
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_end_to_end_against_reference_ties(name, cuda_device):
+    """Whole pipeline through fpb_search_batch vs the op-for-op oracle (torch tie order)."""
+    oidx, didx, queries, params, st = _setup(name, cuda_device)
+    ids, scores, counts = didx.search(queries.half().to(cuda_device), params)
+    torch.cuda.synchronize()
+    ids, scores, counts = ids.cpu(), scores.cpu(), counts.cpu()
+    # the staged run and the one-call run agree bit for bit
+    assert torch.equal(ids, st["ids"].cpu()) and torch.equal(counts, st["counts"].cpu())
+    strict = 0
+    outside = 0
+    for b in range(queries.shape[0]):
+        ref = po.search_one(queries[b], oidx, params.n_ivf_probe, 2000, params.n_full_scores, 10**9,
+                            ties="torch", return_stages=True)
+        n = int(counts[b])
+        assert n == min(params.top_k, len(ref["ids"]))
+        score_of = dict(zip(ref["ids"], ref["scores"]))
+        n_ref = len(score_of)
+        ok, why = ranking_consistent(ids[b, :n].tolist(), scores[b, :n].tolist(), score_of, 1e-3,
+                                     fallback=lambda d, b=b: float(oracle_exact_scores(oidx, queries[b], [d])[0]))
+        assert ok, f"query {b}: {why}"
+        outside += len(score_of) - n_ref
+        strict += int(ids[b, :n].tolist() == ref["ids"][:n])
+        assert (ids[b, n:] == -1).all()
+    # informational: how often the id lists are identical outright
+    print(f"[{name}] strict id-list equality on {strict}/{queries.shape[0]} queries; "
+          f"{outside} returned docs outside the reference's re-ranked set (topk-boundary ties)")
+    assert outside <= max(1, queries.shape[0] // 4)
+
+
+def test_host_path_matches_device_path(cuda_device):
+    oidx, didx, queries, params, st = _setup("base", cuda_device)
+    h_ids, h_scores, h_counts = didx.search_host(queries.half().pin_memory(), params)
+    assert torch.equal(h_ids, st["ids"].cpu())
+    assert torch.equal(h_counts, st["counts"].cpu())
+    assert torch.equal(h_scores, st["scores"].cpu())
+
+
+def test_same_query_twice_is_deterministic(cuda_device):
+    oidx, didx, queries, params, st = _setup("base", cuda_device)
+    a = didx.search(queries.half().to(cuda_device), params)
+    b = didx.search(queries.half().to(cuda_device), params)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_top_k_larger_than_index(cuda_device):
+    """tests/test.py:880-886 of the reference: fewer than top_k results, never more than N."""
+    from fast_plaid_b200.engine import DeviceIndex
+
+    oidx, didx, queries, _, _ = _setup("probe1", cuda_device)
+    params = DeviceIndex.make_params(2000, 4096, 8)
+    ids, scores, counts = didx.search(queries.half().to(cuda_device), params)
+    torch.cuda.synchronize()
+    assert int(counts.max()) <= oidx.doc_lengths.shape[0]
+    for b in range(queries.shape[0]):
+        n = int(counts[b])
+        s = scores[b, :n].cpu()
+        assert bool((s[:-1] >= s[1:]).all())  # tests/test.py:939-954 sorted descending
+        assert len(set(ids[b, :n].tolist())) == n
+
+
+def test_reconstruct_matches_oracle(cuda_device):
+    oidx, didx, queries, params, st = _setup("base", cuda_device)
+    docs = [0, 5, 17, 999]
+    got = didx.reconstruct(docs)
+    torch.cuda.synchronize()
+    bad = 0
+    tot = 0
+    for d, g in zip(docs, got):
+        sel = torch.tensor([d])
+        codes, _ = po.ragged_lookup(oidx.doc_codes, oidx.doc_offsets, oidx.doc_lengths, sel)
+        res, _ = po.ragged_lookup(oidx.doc_residuals, oidx.doc_offsets, oidx.doc_lengths, sel)
+        ref = po.decompress_residuals(res, oidx.bucket_weights, oidx.byte_reversed_bits_map,
+                                      oidx.bucket_weight_indices_lookup, codes, oidx.centroids, oidx.dim, oidx.nbits)
+        dlt = fp16_ulp_diff(g.cpu(), ref)
+        assert int(dlt.max()) <= 1
+        bad += int((dlt > 0).sum())
+        tot += dlt.numel()
+    assert bad / tot < 5e-3
+
+
+def test_compress_only_index_refuses_search(cuda_device):
+    """tests/test.py:748-761 of the reference."""
+    from fast_plaid_b200.engine import DeviceIndex, IndexTensors
+
+    oidx, _, queries, params, _ = _setup("probe1", cuda_device)
+    t = to_index_tensors(oidx)
+    t = IndexTensors(t.nbits, t.centroids, t.bucket_weights, t.doc_lengths, t.doc_codes, t.doc_residuals, None, None)
+    d = DeviceIndex(t, cuda_device)
+    with pytest.raises(ValueError, match="compress_only"):
+        d.search(queries.half().to(cuda_device), params)
