@@ -1,0 +1,533 @@
+#!/usr/bin/env python
+"""Benchmark of the PLAID search hot path (BASELINE.json metric: queries/sec @ top_k=100 on a
+1M-doc x 300-tok x 128-dim index; MaxSim HBM GB/s vs roofline).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                # B200 engine (default)
+    python bench.py --impl reference --gpus 1 --steps 5 --warmup 3   # the reference's CPU path
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   # document-sharded
+
+A "step" is one batch of 64 queries x 32 tokens through the whole hot path.  `value` is
+queries/sec with the queries already resident in HBM; `e2e` is the same through the
+user-facing call with HOST buffers (fp32 queries on the host in, Python lists of
+(doc_id, score) out -- host<->device copies inside the timed region).  One JSON line on stdout.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: n_docs, doc_len, B, Q, top_k
+    "cfg3": dict(n_docs=1_000_000, doc_len=300, B=64, Q=32, top_k=100,
+                 desc="1M docs x 300 tok x 128-dim (nbits=4, K=262144), batch=64 queries x 32 tok, top_k=100"),
+    "cfg2": dict(n_docs=100_000, doc_len=300, B=64, Q=32, top_k=100,
+                 desc="100k docs x 300 tok x 128-dim (nbits=4, K=65536), batch=64 queries x 32 tok, top_k=100"),
+    "cfg4": dict(n_docs=1_000_000, doc_len=300, B=256, Q=32, top_k=1000,
+                 desc="1M docs x 300 tok x 128-dim sharded, batch=256 queries x 32 tok, top_k=1000"),
+    "cfg5": dict(n_docs=50_000, doc_len=1024, B=32, Q=64, top_k=10,
+                 desc="ColPali shape: 50k docs x 1024 tok x 128-dim, batch=32 queries x 64 tok, top_k=10"),
+    "tiny": dict(n_docs=20_000, doc_len=100, B=16, Q=32, top_k=10,
+                 desc="20k docs x 100 tok (plumbing check)"),
+}
+DIM, NBITS, N_IVF_PROBE, N_FULL = 128, 4, 8, 4096
+SEED_INDEX, SEED_QUERY = 1234, 4321
+N_QUERY_BATCHES = 4  # distinct query batches rotated across steps
+
+
+# ----------------------------------------------------------------------------------------
+def measured_peak_hbm() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu = gpu_index
+        self.lines: list[str] = []
+        self.proc: subprocess.Popen | None = None
+        self.thread: threading.Thread | None = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:  # type: ignore[union-attr]
+                self.lines.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def make_query_batches(didx, cfg, n_batches: int, device: str) -> torch.Tensor:
+    """fp32 host queries [n_batches, B, Q, D]: noisy copies of decompressed document tokens
+    (so the top documents are well separated, like real retrieval)."""
+    g = torch.Generator().manual_seed(SEED_QUERY)
+    B, Q = cfg["B"], cfg["Q"]
+    n = n_batches * B
+    doc_ids = torch.randint(0, didx.num_documents, (n,), generator=g).tolist()
+    embs = didx.reconstruct(doc_ids)
+    out = torch.empty(n, Q, DIM)
+    for i, e in enumerate(embs):
+        e = e.float().cpu()
+        rows = torch.randint(0, max(1, e.shape[0]), (Q,), generator=g)
+        x = e[rows] + 0.2 * torch.randn(Q, DIM, generator=g)
+        out[i] = torch.nn.functional.normalize(x, dim=-1)
+    return out.view(n_batches, B, Q, DIM)
+
+
+def maxsim_algorithmic_bytes(didx, views, lay) -> int:
+    """per query T_r*(pd+4) + R*8 + Q*D*2 + R*4, centroid table once per batch."""
+    pd = DIM * NBITS // 8
+    lens = (didx.doc_offsets[1:] - didx.doc_offsets[:-1])
+    total = 0
+    n_rr = views["n_rerank"].cpu()
+    for b in range(lay.B):
+        r = int(n_rr[b])
+        ids = views["rerank"][b, :r].long()
+        t_r = int(lens[ids].sum()) if r > 0 else 0
+        total += t_r * (pd + 4) + r * 8 + lay.Q * DIM * 2 + r * 4
+    return total + didx.num_centroids * DIM * 2
+
+
+def approx_algorithmic_bytes(didx, views, lay) -> tuple[int, int]:
+    """HBM bytes (codes + ids + scores) and L2 gather bytes of the approximate stage."""
+    lens = (didx.doc_offsets[1:] - didx.doc_offsets[:-1])
+    hbm = gather = 0
+    n_c = views["n_cand"].cpu()
+    for b in range(lay.B):
+        n = int(n_c[b])
+        ids = views["cand"][b, :n].long()
+        t_c = int(lens[ids].sum()) if n > 0 else 0
+        hbm += t_c * 4 + n * 12
+        gather += t_c * lay.Qp * 2
+    return hbm, gather
+
+
+# ----------------------------------------------------------------------------------------
+def run_b200(args) -> dict:
+    from fast_plaid_b200.engine import DeviceIndex, _check
+    from fast_plaid_b200.index.synthetic import synthetic_index
+    from fast_plaid_b200.search.fast_plaid import _results_to_lists
+
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the engine)")
+    device = f"cuda:{local}"
+    torch.cuda.set_device(local)
+    cfg = CONFIGS[args.config]
+    n_docs = cfg["n_docs"]
+    lo, hi = (n_docs * rank) // world, (n_docs * (rank + 1)) // world
+    t0 = time.time()
+    data, base = synthetic_index(n_docs, cfg["doc_len"], DIM, NBITS, device, SEED_INDEX, doc_range=(lo, hi))
+    didx = DeviceIndex(data, device, doc_id_base=base)
+    del data
+    torch.cuda.synchronize()
+    t_index = time.time() - t0
+    params = DeviceIndex.make_params(cfg["top_k"], N_FULL, N_IVF_PROBE)
+    B, Q = cfg["B"], cfg["Q"]
+
+    # queries: rank 0 makes them from its shard, everybody gets the same ones
+    if rank == 0:
+        q_host = make_query_batches(didx, cfg, N_QUERY_BATCHES, device)
+    else:
+        q_host = torch.empty(N_QUERY_BATCHES, B, Q, DIM)
+    if world > 1:
+        import torch.distributed as dist
+
+        qd = q_host.to(device)
+        dist.broadcast(qd, 0)
+        q_host = qd.cpu()
+    q_host = q_host.pin_memory()
+    q_dev16 = q_host.to(device).half()
+
+    lib = didx._lib
+    import ctypes
+
+    buf, lay = didx.workspace(B, Q, params)
+    pp = ctypes.byref(params)
+    st = didx._stream()
+    k = params.top_k
+    ids = torch.empty((B, k), dtype=torch.int64, device=device)
+    scores = torch.empty((B, k), dtype=torch.float32, device=device)
+    counts = torch.empty((B,), dtype=torch.int32, device=device)
+    rec = torch.empty((B, lay.R, 16), dtype=torch.uint8, device=device)
+    gathered = torch.empty((world, B, lay.R, 16), dtype=torch.uint8, device=device)
+    stage_names = ["centroid_scores", "probe", "candidates", "approx", "select", "maxsim", "final"]
+
+    def one_step(qb: torch.Tensor, events: list | None) -> None:
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+
+        mark()
+        _check(lib.fpb_stage_centroid_scores(didx._handle, qb.data_ptr(), B, Q, pp, buf.data_ptr(), buf.numel(), st))
+        mark()
+        _check(lib.fpb_stage_probe(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), st))
+        mark()
+        _check(lib.fpb_stage_candidates(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), st))
+        mark()
+        _check(lib.fpb_stage_approx(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), st))
+        mark()
+        _check(lib.fpb_stage_select(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), st))
+        mark()
+        _check(lib.fpb_stage_maxsim(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), st))
+        mark()
+        if world == 1:
+            _check(lib.fpb_stage_rank(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), ids.data_ptr(),
+                                      scores.data_ptr(), counts.data_ptr(), st))
+        else:
+            import torch.distributed as dist
+
+            _check(lib.fpb_stage_records(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), rec.data_ptr(), st))
+            dist.all_gather_into_tensor(gathered.view(-1), rec.view(-1))
+            _check(lib.fpb_merge_shards(gathered.data_ptr(), world, B, lay.R, k, ids.data_ptr(), scores.data_ptr(),
+                                        counts.data_ptr(), st))
+        mark()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        one_step(q_dev16[w % N_QUERY_BATCHES], None)
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    all_events: list[list] = []
+    barrier()
+    t_wall0 = time.time()
+    for s in range(args.steps):
+        ev: list = []
+        one_step(q_dev16[s % N_QUERY_BATCHES], ev)
+        all_events.append(ev)
+    barrier()
+    t_wall = time.time() - t_wall0
+    total_ms = all_events[0][0].elapsed_time(all_events[-1][-1])
+    stage_ms = [0.0] * len(stage_names)
+    for ev in all_events:
+        for i in range(len(stage_names)):
+            stage_ms[i] += ev[i].elapsed_time(ev[i + 1])
+    stage_ms = [x / args.steps for x in stage_ms]
+    views = didx.views(buf, lay)
+    ms_bytes = maxsim_algorithmic_bytes(didx, views, lay)
+    ap_hbm, ap_gather = approx_algorithmic_bytes(didx, views, lay)
+    n_cand_mean = float(views["n_cand"].float().mean())
+
+    # ---- e2e: host fp32 queries in -> Python lists out, copies inside the timed region ----
+    def e2e_call(qb_host: torch.Tensor):
+        q16 = qb_host.to(torch.float16)  # the reference casts on the host (fast_plaid.py:241)
+        if world == 1:
+            h = didx.search_host(q16.pin_memory() if not q16.is_pinned() else q16, params)
+            return _results_to_lists(*h)
+        import torch.distributed as dist
+
+        qd = q16.pin_memory().to(device, non_blocking=True)
+        r = didx.search_records(qd, params)
+        dist.all_gather_into_tensor(gathered.view(-1), r.view(-1))
+        i2, s2, c2 = didx.merge_records(gathered, k)
+        return _results_to_lists(i2.cpu(), s2.cpu(), c2.cpu())
+
+    for w in range(max(1, min(args.warmup, 2))):
+        e2e_call(q_host[w % N_QUERY_BATCHES])
+    barrier()
+    t0 = time.time()
+    for s in range(args.steps):
+        res = e2e_call(q_host[s % N_QUERY_BATCHES])
+    barrier()
+    t_e2e = time.time() - t0
+    clocks = sampler.stop()
+
+    # max over ranks
+    tt = torch.tensor([total_ms, t_e2e * 1000.0], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(tt[0]), float(tt[1])
+
+    peak, peak_src = measured_peak_hbm()
+    ms_time = stage_ms[5] / 1000.0
+    achieved = ms_bytes / ms_time / 1e9 if ms_time > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(args.config, {}).get("k5_maxsim_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    h2d = B * Q * DIM * 2
+    d2h = B * k * 12 + B * 4
+    out = {
+        "metric": "queries/sec @ top_k=%d, %s-doc/128-dim index; MaxSim HBM GB/s vs roofline" % (
+            cfg["top_k"], "1M" if n_docs == 1_000_000 else str(n_docs)),
+        "value": B * args.steps / (total_ms / 1000.0),
+        "unit": "queries/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f16",
+        "data": "synthetic (seeded direct-layout index: normalised random centroids, uniform codes, uniform "
+                "residual nibbles; queries = noisy copies of decompressed document tokens)",
+        "config": {
+            "workload": f"{args.config}: {cfg['desc']}",
+            "n_ivf_probe": N_IVF_PROBE, "n_full_scores": N_FULL, "reranked_per_query": lay.R,
+            "parallelism": f"document shards x{world}" + (" + NCCL all-gather of per-shard records" if world > 1 else ""),
+            "l2": "inputs larger than L2: 20 GB index, 1.07 GB score table per batch; "
+                  f"{N_QUERY_BATCHES} distinct query batches rotate across steps",
+            "candidates_per_query_mean": n_cand_mean,
+            "index_build_s": round(t_index, 1),
+        },
+        "e2e": {"value": B * args.steps / (e2e_ms / 1000.0), "unit": "queries/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "path": "fp32 host queries -> fp16 cast on host -> fpb_search_batch_host (H2D, search, D2H, sync) -> "
+                        "Python list[list[(doc_id, score)]]"},
+        "gpu_launches": (10 if world == 1 else 11) * args.steps,
+        "clocks": clocks,
+        "roofline": {"kernel": "k5_maxsim_kernel (fused residual decompression + MaxSim)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": stage_ms[5]},
+        "stages_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
+        "approx_stage": {"hbm_bytes_per_launch": ap_hbm, "l2_gather_bytes_per_launch": ap_gather,
+                         "hbm_gbs": ap_hbm / (stage_ms[3] / 1000.0) / 1e9 if stage_ms[3] > 0 else None,
+                         "l2_gather_gbs": ap_gather / (stage_ms[3] / 1000.0) / 1e9 if stage_ms[3] > 0 else None},
+        "wall_s_timed_region": round(t_wall, 3),
+    }
+
+    # ---- CPU baseline: the oracle (op-for-op port of the reference's CPU path) on this host ----
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"], out["parity_sample"] = cpu_baseline(didx, q_host[0], params, res_gpu=None,
+                                                                     n_queries=args.cpu_queries or 2, device=device)
+        except Exception as e:  # never lose the GPU numbers
+            out["cpu_baseline"] = {"error": repr(e)[:300]}
+    return out if rank == 0 else {}
+
+
+def oracle_index_from_device(didx):
+    from oracle import plaid_oracle as po
+
+    lens = (didx.doc_offsets[1:] - didx.doc_offsets[:-1]).cpu()
+    ivf_len = (didx.ivf_offsets[1:] - didx.ivf_offsets[:-1]).cpu()
+    return po.OracleIndex(
+        nbits=didx.nbits,
+        centroids=didx.centroids.cpu(),
+        bucket_weights=didx.bucket_weights.cpu(),
+        ivf=didx.ivf_pids.cpu().to(torch.int64) + 0,
+        ivf_lengths=ivf_len,
+        doc_codes=didx.doc_codes.cpu().to(torch.int64),
+        doc_residuals=didx.doc_residuals.cpu(),
+        doc_lengths=lens,
+    )
+
+
+def cpu_baseline(didx, queries_host: torch.Tensor, params, res_gpu, n_queries: int, device: str):
+    """Time the oracle on the host cores on a bounded sample (the first n queries of the batch)
+    and cross-check the engine against it at full size."""
+    from oracle import plaid_oracle as po
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oidx = oracle_index_from_device(didx)
+    n = max(1, min(n_queries, queries_host.shape[0]))
+    q = queries_host[:n]
+    t0 = time.time()
+    ref = []
+    for i in range(n):
+        ref.append(po.search_one(q[i], oidx, params.n_ivf_probe, 2000, params.n_full_scores, params.top_k, ties="torch"))
+    dt = time.time() - t0
+    # parity of the engine on the same queries (local ids == global ids on one GPU)
+    ids, scores, counts = didx.search(q.half().to(device), params)
+    torch.cuda.synchronize()
+    ids, scores, counts = ids.cpu(), scores.cpu(), counts.cpu()
+    same_lists, overlap, max_rel = 0, 0.0, 0.0
+    for i in range(n):
+        r_ids, r_sc = ref[i]
+        g = ids[i, : int(counts[i])].tolist()
+        same_lists += int(g == r_ids)
+        overlap += len(set(g) & set(r_ids)) / max(1, len(r_ids))
+        sc_of = dict(zip(r_ids, r_sc))
+        for d, s in zip(g, scores[i, : int(counts[i])].tolist()):
+            if d in sc_of:
+                max_rel = max(max_rel, abs(s - sc_of[d]) / max(1.0, abs(sc_of[d])))
+    cb = {"value": n / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+          "sample": f"first {n} queries of the batch, full index, sequential queries, torch intra-op threads={cores}",
+          "seconds": round(dt, 2)}
+    parity = {"queries": n, "identical_id_lists": same_lists, "mean_topk_overlap": overlap / n,
+              "max_rel_score_err_on_common_ids": max_rel}
+    return cb, parity
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(args) -> dict:
+    """The reference's own CPU implementation of the path, i.e. the op-for-op PyTorch-CPU
+    restatement in oracle/ (the Rust extension cannot be built here: no cargo/rustc), timed on
+    the host cores with every thread it can use, on the same config and synthetic index."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    from oracle import plaid_oracle as po
+
+    cfg = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if torch.cuda.is_available():  # the GPU only GENERATES the synthetic index; nothing timed runs on it
+        from fast_plaid_b200.engine import DeviceIndex
+        from fast_plaid_b200.index.synthetic import synthetic_index
+
+        data, _ = synthetic_index(cfg["n_docs"], cfg["doc_len"], DIM, NBITS, "cuda:0", SEED_INDEX)
+        didx = DeviceIndex(data, "cuda:0")
+        del data
+        q_host = make_query_batches(didx, cfg, N_QUERY_BATCHES, "cuda:0")
+        oidx = oracle_index_from_device(didx)
+        didx.close()
+        del didx
+        torch.cuda.empty_cache()
+    else:
+        return {"impl": "reference", "unavailable": "no CUDA device to generate the synthetic index"}
+    B = cfg["B"]
+    # bounded sample: as many queries per step as fit in ~10 s, measured on one warm-up query
+    t0 = time.time()
+    po.search_one(q_host[0, 0], oidx, N_IVF_PROBE, 2000, N_FULL, cfg["top_k"])
+    t_one = time.time() - t0
+    per_step = max(1, min(B, int(10.0 / max(t_one, 1e-3))))
+    if args.cpu_queries:
+        per_step = max(1, min(B, args.cpu_queries))
+
+    def step(s: int) -> None:
+        qb = q_host[s % N_QUERY_BATCHES]
+        for i in range(per_step):
+            po.search_one(qb[i], oidx, N_IVF_PROBE, 2000, N_FULL, cfg["top_k"])
+
+    for w in range(min(args.warmup, 1)):
+        step(w)
+    t0 = time.time()
+    for s in range(args.steps):
+        step(s)
+    dt = time.time() - t0
+    val = per_step * args.steps / dt
+    return {
+        "impl": "reference",
+        "metric": "queries/sec @ top_k=%d, %s-doc/128-dim index; MaxSim HBM GB/s vs roofline" % (
+            cfg["top_k"], "1M" if cfg["n_docs"] == 1_000_000 else str(cfg["n_docs"])),
+        "value": val, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1000.0, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic (same seeded index and queries as the b200 arm)",
+        "config": {"workload": f"{args.config}: {cfg['desc']}", "n_ivf_probe": N_IVF_PROBE, "n_full_scores": N_FULL,
+                   "parallelism": "host CPU"},
+        "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} queries per step (of the {B}-query batch), full index, "
+                                   f"torch intra-op threads={cores}; one warm-up step"},
+        "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", choices=list(CONFIGS), default="cfg3")
+    ap.add_argument("--cpu-queries", type=int, default=0, help="queries timed on the CPU (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    out = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if out:
+        print(json.dumps(out))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

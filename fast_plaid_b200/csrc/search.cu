@@ -159,3 +159,12 @@ extern "C" int fpb_stage_rank(const fpb_index* ix, int B, int Q, const fpb_param
   }
   return launch_rank(ix, ws, p->top_k, d_out_ids, d_out_scores, d_out_counts, st);
 }
+extern "C" int fpb_stage_records(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                                 size_t ws_bytes, fpb_record* d_records, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  if (!d_records) {
+    fpb_set_error("fpb_stage_records: NULL record pointer");
+    return FPB_ERR_INVALID;
+  }
+  return launch_emit_records(ix, ws, d_records, st);
+}

@@ -86,6 +86,7 @@ EXPORTED_SYMBOLS = [
     "fpb_stage_select",
     "fpb_stage_maxsim",
     "fpb_stage_rank",
+    "fpb_stage_records",
     "fpb_search_shard",
     "fpb_merge_shards",
     "fpb_reconstruct",
@@ -136,6 +137,8 @@ def load_library() -> ctypes.CDLL:
             fn.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
         lib.fpb_stage_rank.restype = i32
         lib.fpb_stage_rank.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp, vp, vp]
+        lib.fpb_stage_records.restype = i32
+        lib.fpb_stage_records.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
         lib.fpb_search_shard.restype = i32
         lib.fpb_search_shard.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
         lib.fpb_merge_shards.restype = i32

@@ -1,0 +1,92 @@
+"""Direct synthetic-index generator for benchmark-sized indexes.
+
+A 1M-document x 300-token index has 3e8 tokens (76.8 GB of raw fp16 embeddings): running
+k-means and the encoder over it just to obtain a benchmark input is not what the metric
+measures.  This generator writes the index *layout* directly, chunk by chunk and seeded per
+chunk so that any document range (a shard) can be produced independently and the union over
+ranks is the same index:
+
+  centroids   L2-normalised randn(K, dim), K = 2^floor(log2(16*sqrt(E)))   (fast_plaid.py:152-154)
+  codes       uniform over [0, K)  -- the statistical worst case for the candidate stage: every
+              document touches ~len distinct cells, so probing 8 cells x 32 tokens reaches about
+              a quarter of a 1M-document index (SURVEY.md 8d "uniform-random model")
+  residuals   uniform random bytes = every bucket equally likely, which is what quantile
+              cutoffs produce on the data they were trained on (create.rs:352-357)
+  weights     the (i+0.5)/2^nbits quantiles of N(0, sigma^2)                 (create.rs:359-364)
+  ivf         per centroid the sorted unique ids of the documents using it   (create.rs:528-559)
+
+The decompressed tokens are centroid + per-dimension quantised Gaussian noise, renormalised,
+i.e. a valid PLAID index of a clustered corpus.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ..engine import IndexTensors
+from . import build
+
+
+def _normal_quantiles(n: int, sigma: float) -> torch.Tensor:
+    p = (torch.arange(n, dtype=torch.float64) + 0.5) / n
+    return (sigma * math.sqrt(2.0) * torch.erfinv(2.0 * p - 1.0)).float()
+
+
+@torch.inference_mode()
+def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, device: str = "cuda:0",
+                    seed: int = 1234, doc_range: tuple[int, int] | None = None, ragged: bool = False,
+                    sigma: float = 0.05, docs_per_chunk: int = 25_000) -> tuple[IndexTensors, int]:
+    """Returns (tensors on `device`, doc_id_base).  `doc_range=(lo, hi)` generates only that
+    slice of the global index (document sharding); ids in the IVF are then local."""
+    dev = torch.device(device)
+    lo, hi = (0, n_docs) if doc_range is None else doc_range
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    # document lengths of the WHOLE index (cheap) so that K and the chunk seeds are global
+    if ragged:
+        gl = torch.Generator().manual_seed(seed + 1)
+        lengths = torch.randint(max(1, doc_len // 4), doc_len + 1, (n_docs,), generator=gl)
+    else:
+        lengths = torch.full((n_docs,), doc_len, dtype=torch.int64)
+    total_tokens = int(lengths.sum())
+    K = build.num_partitions_for(float(total_tokens))
+    centroids = torch.nn.functional.normalize(torch.randn(K, dim, generator=g, device=dev), dim=-1).half()
+    weights = _normal_quantiles(2**nbits, sigma).to(dev).half()
+    pd = dim * nbits // 8
+    my_lengths = lengths[lo:hi]
+    n_tok = int(my_lengths.sum())
+    codes = torch.empty(max(n_tok, 1), dtype=torch.int32, device=dev)
+    residuals = torch.empty((max(n_tok, 1), pd), dtype=torch.uint8, device=dev)
+    offs = torch.zeros(n_docs + 1, dtype=torch.int64)
+    offs[1:] = lengths.cumsum(0)
+    t_base = int(offs[lo])
+    for c0 in range((lo // docs_per_chunk) * docs_per_chunk, hi, docs_per_chunk):
+        c1 = min(c0 + docs_per_chunk, n_docs)
+        gc = torch.Generator(device=dev)
+        gc.manual_seed(seed * 1_000_003 + c0)
+        n = int(offs[c1] - offs[c0])
+        cc = torch.randint(0, K, (n,), generator=gc, device=dev, dtype=torch.int32)
+        rr = torch.randint(0, 256, (n, pd), generator=gc, device=dev, dtype=torch.uint8)
+        # clip the chunk to [lo, hi)
+        a = max(c0, lo)
+        b = min(c1, hi)
+        s0 = int(offs[a] - offs[c0])
+        s1 = int(offs[b] - offs[c0])
+        d0 = int(offs[a]) - t_base
+        codes[d0 : d0 + (s1 - s0)] = cc[s0:s1]
+        residuals[d0 : d0 + (s1 - s0)] = rr[s0:s1]
+        del cc, rr
+    ivf, ivf_lengths = build.build_ivf(codes[:n_tok], my_lengths, K)
+    data = IndexTensors(
+        nbits=nbits,
+        centroids=centroids,
+        bucket_weights=weights,
+        doc_lengths=my_lengths,
+        doc_codes=codes[:n_tok] if n_tok > 0 else codes[:0],
+        doc_residuals=residuals[:n_tok] if n_tok > 0 else residuals[:0],
+        ivf=ivf.to(torch.int32),
+        ivf_lengths=ivf_lengths,
+    )
+    return data, lo

@@ -38,6 +38,7 @@ extern "C" {
 #define FPB_ERR_NO_IVF (-5)   /* compress_only index: search refused (search.rs:227-232) */
 
 typedef struct fpb_index fpb_index;
+struct fpb_record;
 
 /* Thread-local message of the last failing call in this thread. */
 const char* fpb_last_error(void);
@@ -144,16 +145,20 @@ int fpb_stage_rank(const fpb_index*, int B, int Q, const fpb_params*, void* d_wo
                    size_t, int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts,
                    void* stream); /* search.rs:659-666 */
 
+int fpb_stage_records(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace, size_t,
+                      struct fpb_record* d_records, void* stream); /* sharded mode: emit [B, R] records */
+
 /* ---- document-sharded search (new; the reference replicates the index and splits the
  * query list, fast_plaid.py:893-928).  Each rank runs fpb_search_shard on its shard and
  * emits R fixed-size records per query; the host all-gathers them (NCCL) and every rank
  * runs fpb_merge_shards, which re-applies the reference's GLOBAL pruning rule
  * (top n_full_scores/4 by approximate score, search.rs:605-619) before the final sort. */
-typedef struct fpb_record {
+struct fpb_record {
   float approx;   /* -inf for padding */
   float exact;
   int64_t doc_id; /* global id, -1 for padding */
-} fpb_record;
+};
+typedef struct fpb_record fpb_record;
 
 int fpb_search_shard(const fpb_index* index, const void* d_queries, int B, int Q,
                      const fpb_params* params, void* d_workspace, size_t workspace_bytes,
