@@ -1,0 +1,139 @@
+"""GPU tests through the public surface: FastPlaid create/search/update/delete on a CUDA
+device, the committed golden fixtures, and the sharded path (two shards on one GPU)."""
+
+from __future__ import annotations
+
+import glob
+import os
+
+import pytest
+import torch
+
+from util import (build_oracle_index, make_docs, make_queries, oracle_exact_scores, ranking_consistent,
+                  to_index_tensors)
+
+from oracle import plaid_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_engine_reproduces_golden_fixtures(path, cuda_device):
+    """Committed vectors (minted by the oracle, tests/golden/make_golden.py): integer stages
+    exactly, scores to 1e-3 relative, ranking consistent."""
+    from fast_plaid_b200.engine import DeviceIndex, IndexTensors
+
+    blob = torch.load(path, weights_only=False)
+    ix, m = blob["index"], blob["meta"]
+    didx = DeviceIndex(IndexTensors(ix["nbits"], ix["centroids"], ix["bucket_weights"], ix["doc_lengths"],
+                                    ix["doc_codes"], ix["doc_residuals"], ix["ivf"], ix["ivf_lengths"]), cuda_device)
+    params = DeviceIndex.make_params(m["top_k"], m["n_full"], m["n_probe"])
+    st = didx.run_stages(blob["queries"].to(cuda_device), params)
+    torch.cuda.synchronize()
+    n_strict = 0
+    for b, exp in enumerate(blob["expected"]):
+        cells = torch.unique(st["cells"][b].cpu().flatten().long())
+        n = int(st["n_cand"][b])
+        r = int(st["n_rerank"][b])
+        n_ids = int(st["counts"][b])
+        got_ids = st["ids"][b, :n_ids].cpu().tolist()
+        got_sc = st["scores"][b, :n_ids].cpu().tolist()
+        # S can differ from the CPU by one fp16 ulp on ~1e-4 of its entries, which may move a
+        # boundary cell / candidate; anything that does not match exactly must still be a valid
+        # ranking of the oracle's scores
+        exact_match = (torch.equal(cells[cells >= 0], exp["cells"]) and
+                       torch.equal(st["cand"][b, :n].cpu().long(), exp["candidates"]) and
+                       torch.equal(st["rerank"][b, :r].cpu().long(), exp["rerank"]))
+        n_strict += int(exact_match and got_ids == exp["ids"])
+        if exact_match:
+            assert torch.allclose(st["exact"][b, :r].cpu(), exp["exact"], rtol=1e-3, atol=1e-3)
+        score_of = dict(zip(exp["ids"], exp["scores"]))
+        oix = po.OracleIndex(ix["nbits"], ix["centroids"], ix["bucket_weights"], ix["ivf"].long(),
+                             ix["ivf_lengths"].long(), ix["doc_codes"].long(), ix["doc_residuals"], ix["doc_lengths"].long())
+        ok, why = ranking_consistent(got_ids, got_sc, score_of, 1e-3,
+                                     fallback=lambda d, b=b: float(oracle_exact_scores(oix, blob["queries"][b].float(), [d])[0]))
+        assert ok, why
+    assert n_strict >= len(blob["expected"]) - 1, f"only {n_strict} queries matched the golden vectors exactly"
+
+
+def test_fastplaid_surface_on_gpu(tmp_path, cuda_device):
+    """create -> search -> update -> delete -> get_embeddings through the FastPlaid class, on
+    the same structural checks as the reference's tests (tests/test.py:31-104, 202-389)."""
+    from fast_plaid_b200 import search
+    from fast_plaid_b200.index import store
+
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device=cuda_device)
+    docs = make_docs(300, 20, 80, seed=11)
+    fp.create(docs, kmeans_niters=4)
+    queries = make_queries(10, 30, seed=12, docs=docs)
+    res = fp.search(queries, top_k=10)
+    assert len(res) == 10 and all(len(r) == 10 for r in res)  # tests/test.py:44-49
+    assert all(isinstance(d, int) and isinstance(s, float) for r in res for d, s in r)
+    # the same directory, searched by the oracle
+    data = store.read_index(path)
+    oidx = po.OracleIndex(data.nbits, data.centroids, data.bucket_weights, data.ivf, data.ivf_lengths.long(),
+                          data.doc_codes, data.doc_residuals, data.doc_lengths)
+    for b in range(10):
+        ref = po.search_one(queries[b], oidx, top_k=10**9, return_stages=True)
+        ok, why = ranking_consistent([d for d, _ in res[b]], [s for _, s in res[b]], dict(zip(ref["ids"], ref["scores"])), 1e-3,
+                                     fallback=lambda d, b=b: float(oracle_exact_scores(oidx, queries[b], [d])[0]))
+        assert ok, why
+    # list-of-tensors input is zero padded like the reference (fast_plaid.py:772-780)
+    res_list = fp.search([queries[0][:20], queries[1]], top_k=5)
+    assert len(res_list) == 2 and all(len(r) == 5 for r in res_list)
+    # top_k beyond the index size (tests/test.py:880-886)
+    big = fp.search(queries[:2], top_k=1000)
+    assert all(0 < len(r) <= 300 for r in big)
+    # update then delete keep ids in range (tests/test.py:218-238, 363-368)
+    fp.update(make_docs(50, 20, 80, seed=13))
+    res = fp.search(queries, top_k=10)
+    assert all(0 <= d < 350 for r in res for d, _ in r)
+    fp.delete(list(range(0, 100)))
+    res = fp.search(queries, top_k=10)
+    assert all(0 <= d < 250 for r in res for d, _ in r)
+    # get_embeddings returns unit-norm rows of the right length
+    embs = fp.get_embeddings([0, 7])
+    lens = store.read_index(path).doc_lengths
+    assert [e.shape[0] for e in embs] == [int(lens[0]), int(lens[7])]
+    assert torch.allclose(embs[0].float().norm(dim=-1), torch.ones(embs[0].shape[0]), atol=2e-3)
+    # token-score matrices (tests/test.py:109-197)
+    ts = fp.search_token_scores(queries[:2], top_k=3)
+    plain = fp.search(queries[:2], top_k=3)
+    for rq, rp in zip(ts, plain):
+        assert [d for d, _, _ in rq] == [d for d, _ in rp]
+        for d, s, m in rq:
+            assert m.shape == (30, int(store.read_index(path).doc_lengths[d]))
+            assert abs(float(m.float().max(dim=1).values.sum()) - s) < 0.1
+    # non-3D tensor -> ValueError (search.rs:234-239)
+    with pytest.raises(ValueError):
+        fp.search(queries[0], top_k=5)
+    fp.close()
+
+
+def test_two_shards_on_one_gpu_equal_the_unsharded_search(cuda_device):
+    """fpb_search_shard x2 + fpb_merge_shards == fpb_search_batch, bit for bit."""
+    from fast_plaid_b200.engine import DeviceIndex, shard_tensors
+
+    docs = make_docs(900, 10, 60, seed=21)
+    oidx, _ = build_oracle_index(docs)
+    t = to_index_tensors(oidx)
+    whole = DeviceIndex(t, cuda_device)
+    queries = make_queries(6, 32, seed=22, docs=docs).half().to(cuda_device)
+    for n_full, top_k in ((64, 10), (4096, 50)):
+        params = DeviceIndex.make_params(top_k, n_full, 8)
+        ids, scores, counts = whole.search(queries, params)
+        for world in (2, 3):
+            recs = []
+            for r in range(world):
+                sh, base = shard_tensors(t, r, world)
+                d = DeviceIndex(sh, cuda_device, doc_id_base=base)
+                recs.append(d.search_records(queries, params))
+            gathered = torch.stack(recs)
+            i2, s2, c2 = whole.merge_records(gathered, top_k)
+            torch.cuda.synchronize()
+            assert torch.equal(c2, counts)
+            assert torch.equal(i2, ids), f"world={world} n_full={n_full}"
+            assert torch.equal(s2, scores)

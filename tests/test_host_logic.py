@@ -1,0 +1,124 @@
+"""Host-side behaviour of the FastPlaid surface that needs no GPU: index bookkeeping through
+create / update / delete, argument handling, and the loud failure of search on a CPU device
+(structural checks borrowed from the reference's tests/test.py)."""
+
+from __future__ import annotations
+
+import json
+import os
+
+import pytest
+import torch
+
+from util import make_docs
+
+from fast_plaid_b200 import search
+from fast_plaid_b200.engine import EngineUnavailableError
+from fast_plaid_b200.index import store
+
+
+def _meta(path):
+    return json.load(open(os.path.join(path, "metadata.json")))
+
+
+def test_create_update_delete_bookkeeping(tmp_path):
+    """tests/test.py:977-1303 of the reference: metadata.json num_documents follows the index."""
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    docs = make_docs(60, 5, 30, seed=1)
+    fp.create(docs, kmeans_niters=2)
+    assert _meta(path)["num_documents"] == 60
+    assert os.path.exists(os.path.join(path, "embeddings.npy"))  # <= start_from_scratch docs keep raw copies
+    fp.update(make_docs(15, 5, 30, seed=2))
+    assert _meta(path)["num_documents"] == 75
+    data = store.read_index(path)
+    assert data.num_documents == 75 and int(data.doc_lengths.sum()) == data.doc_codes.shape[0]
+    fp.delete([0, 3, 74])
+    data = store.read_index(path)
+    assert _meta(path)["num_documents"] == 72 and data.num_documents == 72
+    assert int(data.ivf.max()) < 72
+    assert int(data.doc_lengths.sum()) == data.doc_codes.shape[0] == _meta(path)["num_embeddings"]
+
+
+def test_update_appends_with_existing_codec_when_large(tmp_path):
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    docs = make_docs(40, 5, 30, seed=1)
+    fp.create(docs, kmeans_niters=2, start_from_scratch=10)  # no embeddings.npy kept
+    assert not os.path.exists(os.path.join(path, "embeddings.npy"))
+    cent_before = store.read_index(path).centroids.clone()
+    fp.update(make_docs(12, 5, 30, seed=3), start_from_scratch=10)
+    data = store.read_index(path)
+    assert data.num_documents == 52
+    assert torch.equal(data.centroids, cent_before)  # appended with the existing centroids
+    # every appended document is reachable through the IVF
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), data.doc_lengths.cumsum(0)])
+    for d in (40, 51):
+        codes = set(data.doc_codes[offs[d]:offs[d + 1]].tolist())
+        ivf_offs = torch.cat([torch.zeros(1, dtype=torch.int64), data.ivf_lengths.long().cumsum(0)])
+        for c in codes:
+            assert d in data.ivf[ivf_offs[c]:ivf_offs[c + 1]].tolist()
+
+
+def test_update_on_missing_index_creates_it(tmp_path):
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    fp.update(make_docs(20, 5, 30, seed=4), kmeans_niters=2)
+    assert _meta(path)["num_documents"] == 20
+
+
+def test_compress_only_has_no_ivf_files(tmp_path):
+    """tests/test.py:734-746 of the reference."""
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    fp.create(make_docs(30, 5, 30, seed=5), kmeans_niters=2, compress_only=True)
+    assert not os.path.exists(os.path.join(path, "ivf.npy"))
+    assert not os.path.exists(os.path.join(path, "ivf_lengths.npy"))
+    assert _meta(path)["compress_only"] is True
+    assert store.read_index(path).ivf is None
+
+
+def test_search_on_cpu_device_fails_loudly(tmp_path):
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    fp.create(make_docs(30, 5, 30, seed=6), kmeans_niters=2)
+    with pytest.raises(EngineUnavailableError, match="no CPU search path"):
+        fp.search(torch.randn(2, 8, 128), top_k=5)
+
+
+def test_search_without_index_raises_file_not_found(tmp_path):
+    fp = search.FastPlaid(str(tmp_path / "empty"), device="cpu")
+    with pytest.raises(FileNotFoundError):
+        fp.search(torch.randn(1, 4, 128))
+
+
+def test_bad_device_string(tmp_path):
+    with pytest.raises(ValueError, match="Unsupported device"):
+        search.FastPlaid(str(tmp_path / "x"), device="tpu:0")
+
+
+def test_metadata_length_must_match(tmp_path):
+    fp = search.FastPlaid(str(tmp_path / "idx"), device="cpu")
+    with pytest.raises(ValueError, match="metadata"):
+        fp.create(make_docs(5, 5, 10, seed=7), metadata=[{"a": 1}])
+
+
+def test_metadata_table_and_where(tmp_path):
+    from fast_plaid_b200 import filtering
+
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    fp.create(make_docs(12, 5, 10, seed=8), kmeans_niters=1, metadata=[{"lang": "en" if i % 2 else "fr", "n": i} for i in range(12)])
+    assert filtering.where(path, "lang = ?", ("en",)) == [1, 3, 5, 7, 9, 11]
+    fp.delete([1])
+    assert filtering.where(path, "lang = ?", ("en",)) == [2, 4, 6, 8, 10]
+
+
+def test_k_heuristic():
+    from fast_plaid_b200.index.build import num_partitions_for
+
+    # K per BASELINE config
+    assert num_partitions_for(1_000 * 300) == 8192
+    assert num_partitions_for(100_000 * 300) == 65536
+    assert num_partitions_for(1_000_000 * 300) == 262144
+    assert num_partitions_for(50_000 * 1024) == 65536

@@ -101,3 +101,21 @@ def ranking_consistent(gpu_ids, gpu_scores, ref_score_of: dict, tol: float, fall
             return False, f"rank {i}: doc {d} (ref {r}) ranked below a doc with ref {prev}"
         prev = r
     return True, ""
+
+
+def merge_records_host(records: list[tuple[float, float, int]], R: int, top_k: int) -> list[tuple[int, float]]:
+    """Host statement of the sharded merge rule (k6_merge_kernel): keep the R best by
+    (approx desc, doc id asc), order them by (exact desc, doc id asc), emit top_k."""
+    keep = sorted(records, key=lambda r: (-r[0], r[2]))[:R]
+    keep.sort(key=lambda r: (-r[1], r[2]))
+    return [(r[2], r[1]) for r in keep[:top_k]]
+
+
+def shard_records_oracle(shard_index, base: int, query: torch.Tensor, n_probe: int, n_full: int):
+    """What fpb_search_shard emits for one query, computed with the oracle on a shard."""
+    st = plaid_oracle.search_one(query, shard_index, n_probe, 2000, n_full, 10**9, ties="canonical",
+                                 return_stages=True)
+    if len(st.get("ids", [])) == 0 and "rerank" not in st:
+        return []
+    approx_of = dict(zip(st["candidates"].tolist(), st["approx"].tolist()))
+    return [(approx_of[d], float(e), d + base) for d, e in zip(st["rerank"].tolist(), st["exact"].tolist())]
