@@ -560,11 +560,16 @@ def main() -> None:
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries timed on the CPU (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # keep stdout clean for the ONE JSON line: NCCL / libraries may print to fd 1
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     out = run_reference(args) if args.impl == "reference" else run_b200(args)
+    sys.stdout.flush()
     if out:
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
 
