@@ -15,7 +15,7 @@ void fpb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* fpb_last_error(void) { return g_err; }
-extern "C" int fpb_abi_version(void) { return 1; }
+extern "C" int fpb_abi_version(void) { return 2; }
 
 static int bitrev(int x, int nbits) {
   int r = 0;
@@ -161,6 +161,12 @@ extern "C" int fpb_workspace_layout(const fpb_index* ix, int B, int Q, const fpb
   L->off_rerank = take(int64_t(B) * R * 4);
   L->off_rerank_approx = take(int64_t(B) * R * 4);
   L->off_exact = take(int64_t(B) * R * 4);
+  const bool sub = (p->flags & FPB_FLAG_SUBSET) != 0;
+  L->cbitmap_words = int((ix->K + 31) / 32) + 1;
+  L->off_cbitmap = take(sub ? int64_t(B) * L->cbitmap_words * 4 : 0);
+  L->off_clist = take(sub ? int64_t(B) * ix->K * 4 : 0);
+  L->off_n_clist = take(sub ? int64_t(B) * 4 : 0);
+  L->off_sbitmap = take(sub ? int64_t(B) * L->bitmap_words * 4 : 0);
   L->total_bytes = off;
   return FPB_OK;
 }

@@ -213,6 +213,39 @@ k1b_probe_kernel(const __half* __restrict__ S, const __half* __restrict__ tmax, 
   }
 }
 
+// Subset variant (search.rs:494-517): the top-n is taken over the centroids that occur in the
+// subset's documents only (clist, ascending), n = min(n_ivf_probe, #such centroids).
+__global__ void __launch_bounds__(256)
+k1b_probe_subset_kernel(const __half* __restrict__ S, int K, int B, int Q, int Qp, int n_probe,
+                        const int32_t* __restrict__ clist, const int32_t* __restrict__ n_clist,
+                        int32_t* __restrict__ cells) {
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wg >= B * Q) return;
+  const int b = wg / Q, q = wg % Q;
+  const int nc = n_clist[b];
+  const int n = min(n_probe, nc);
+  const int32_t* cl = clist + int64_t(b) * K;
+  const uint16_t* Sb = reinterpret_cast<const uint16_t*>(S) + int64_t(b) * K * Qp + q;
+  uint64_t mine = 0;
+  if (n > 0) {
+    for (int base = 0; base < nc; base += 32) {
+      const int i = base + lane;
+      uint64_t key = 0;
+      if (i < nc) {
+        const int c = cl[i];
+        key = (uint64_t(f16_key(Sb[int64_t(c) * Qp])) << 32) | uint64_t(0xffffffffu - uint32_t(c));
+      }
+      topn_offer(mine, n, key, lane);
+    }
+  }
+  if (lane < n_probe) {
+    int32_t c = -1;
+    if (lane < n && mine != 0) c = int32_t(0xffffffffu - uint32_t(mine));
+    cells[(int64_t(b) * Q + q) * n_probe + lane] = c;
+  }
+}
+
 __global__ void pad_queries_kernel(const __half* __restrict__ q, __half* __restrict__ out, int B, int Q,
                                    int Qp, int D) {
   const int64_t n8 = int64_t(B) * Qp * (D / 8);
@@ -279,10 +312,16 @@ int launch_centroid_scores(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   }
 }
 
-int launch_probe(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+int launch_probe(const fpb_index* ix, const Ws& ws, bool subset, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   const int warps = L.B * L.Q;
   const int blocks = (warps + 7) / 8;
+  if (subset) {
+    k1b_probe_subset_kernel<<<blocks, 256, 0, st>>>(ws.S(), int(ix->K), L.B, L.Q, L.Qp, L.n_probe, ws.clist(),
+                                                    ws.n_clist(), ws.cells());
+    FPB_LAUNCH_CHECK("k1b_probe_subset");
+    return FPB_OK;
+  }
   k1b_probe_kernel<<<blocks, 256, 0, st>>>(ws.S(), ws.tmax(), int(ix->K), L.B, L.Q, L.Qp, L.n_tiles,
                                            L.n_probe, ws.cells());
   FPB_LAUNCH_CHECK("k1b_probe");

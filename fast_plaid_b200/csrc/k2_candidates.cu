@@ -30,12 +30,13 @@ k2_mark_kernel(const int32_t* __restrict__ cells, int slots, const int64_t* __re
 
 // one CTA per query: ordered compaction of the bitmap into cand[b][0..n_cand[b])
 __global__ void __launch_bounds__(1024)
-k2_compact_kernel(const uint32_t* __restrict__ bitmap, int bitmap_words, int32_t* __restrict__ cand,
-                  int cand_cap, int32_t* __restrict__ n_cand) {
+k2_compact_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ mask, int bitmap_words,
+                  int32_t* __restrict__ cand, int cand_cap, int32_t* __restrict__ n_cand) {
   __shared__ int warp_sums[32];
   __shared__ int s_base;
   const int b = blockIdx.x;
   const uint32_t* bm = bitmap + int64_t(b) * bitmap_words;
+  const uint32_t* mk = mask ? mask + int64_t(b) * bitmap_words : nullptr;  // subset intersection (search.rs:544-547)
   int32_t* out = cand + int64_t(b) * cand_cap;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_base = 0;
@@ -43,6 +44,7 @@ k2_compact_kernel(const uint32_t* __restrict__ bitmap, int bitmap_words, int32_t
   for (int w0 = 0; w0 < bitmap_words; w0 += 1024) {
     const int wi = w0 + tid;
     uint32_t w = (wi < bitmap_words) ? bm[wi] : 0u;
+    if (mk && wi < bitmap_words) w &= mk[wi];
     const int c = __popc(w);
     int incl = c;
 #pragma unroll
@@ -77,9 +79,57 @@ k2_compact_kernel(const uint32_t* __restrict__ bitmap, int bitmap_words, int32_t
   if (tid == 0) n_cand[b] = s_base;
 }
 
+// The subset's documents as a bitmap and the centroids occurring in them as a second bitmap
+// (search.rs:496-503: lookup of the subset's codes + unique).  One warp per subset document.
+__global__ void __launch_bounds__(256)
+subset_mark_kernel(const int32_t* __restrict__ ids, const int64_t* __restrict__ offsets,
+                   const int64_t* __restrict__ doc_offsets, const int32_t* __restrict__ codes, int64_t n_docs,
+                   int64_t doc_id_base, uint32_t* __restrict__ sbitmap, int bitmap_words,
+                   uint32_t* __restrict__ cbitmap, int cbitmap_words) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = offsets[b] + int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= offsets[b + 1]) return;
+  const int64_t d = int64_t(ids[i]) - doc_id_base;
+  if (d < 0 || d >= n_docs) return;  // not in this shard / invalid id: ignored
+  if (lane == 0) atomicOr(sbitmap + int64_t(b) * bitmap_words + (d >> 5), 1u << (d & 31));
+  uint32_t* cb = cbitmap + int64_t(b) * cbitmap_words;
+  const int64_t o0 = doc_offsets[d], o1 = doc_offsets[d + 1];
+  for (int64_t t = o0 + lane; t < o1; t += 32) {
+    const int c = __ldg(codes + t);
+    atomicOr(cb + (c >> 5), 1u << (c & 31));
+  }
+}
+
 }  // namespace
 
-int launch_candidates(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+int launch_compact(const uint32_t* bitmap, const uint32_t* mask, int words, int32_t* out, int cap, int32_t* n_out,
+                   int B, cudaStream_t st) {
+  k2_compact_kernel<<<B, 1024, 0, st>>>(bitmap, mask, words, out, cap, n_out);
+  FPB_LAUNCH_CHECK("k2_compact");
+  return FPB_OK;
+}
+
+int launch_subset(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const int64_t* d_offsets,
+                  int64_t max_len, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
+  if (L.off_sbitmap == L.off_cbitmap) {
+    fpb_set_error("subset search needs a workspace laid out with FPB_FLAG_SUBSET");
+    return FPB_ERR_INVALID;
+  }
+  FPB_CUDA_CHECK(cudaMemsetAsync(ws.cbitmap(), 0, size_t(L.B) * L.cbitmap_words * 4, st));
+  FPB_CUDA_CHECK(cudaMemsetAsync(ws.sbitmap(), 0, size_t(L.B) * L.bitmap_words * 4, st));
+  if (max_len > 0) {
+    dim3 grid(unsigned((max_len + 7) / 8), L.B);
+    subset_mark_kernel<<<grid, 256, 0, st>>>(d_ids, d_offsets, ix->doc_offsets, ix->doc_codes, ix->N,
+                                             ix->doc_id_base, ws.sbitmap(), L.bitmap_words, ws.cbitmap(),
+                                             L.cbitmap_words);
+    FPB_LAUNCH_CHECK("subset_mark");
+  }
+  return launch_compact(ws.cbitmap(), nullptr, L.cbitmap_words, ws.clist(), int(ix->K), ws.n_clist(), L.B, st);
+}
+
+int launch_candidates(const fpb_index* ix, const Ws& ws, bool subset, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   FPB_CUDA_CHECK(cudaMemsetAsync(ws.bitmap(), 0, size_t(L.B) * L.bitmap_words * 4, st));
   const int slots = L.Q * L.n_probe;
@@ -87,8 +137,6 @@ int launch_candidates(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   k2_mark_kernel<<<grid, 128, 0, st>>>(ws.cells(), slots, ix->ivf_offsets, ix->ivf_pids, ws.bitmap(),
                                        L.bitmap_words);
   FPB_LAUNCH_CHECK("k2_mark");
-  k2_compact_kernel<<<L.B, 1024, 0, st>>>(ws.bitmap(), L.bitmap_words, ws.cand(), L.cand_cap,
-                                          ws.n_cand());
-  FPB_LAUNCH_CHECK("k2_compact");
-  return FPB_OK;
+  return launch_compact(ws.bitmap(), subset ? ws.sbitmap() : nullptr, L.bitmap_words, ws.cand(), L.cand_cap,
+                        ws.n_cand(), L.B, st);
 }

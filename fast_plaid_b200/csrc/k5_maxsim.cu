@@ -13,6 +13,8 @@
 // (4 B) and the centroid row (L2-resident table).
 //
 // v1 data path: mma.sync m16n8k16 (legacy tensor path) with a CTA of 4 warps per document.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace {
@@ -357,6 +359,13 @@ int launch_k5_q(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
 }  // namespace
 
 int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+  // FPB_K5_V1=1 forces the generic v1 kernel (A/B measurements); both are bit-identical.
+  static const bool force_v1 = getenv("FPB_K5_V1") != nullptr;
+  if (!force_v1) {
+    bool handled = false;
+    const int rc = launch_maxsim_v2(ix, ws, st, &handled);
+    if (rc != FPB_OK || handled) return rc;
+  }
 #define CALL(DD, NB) return launch_k5_q<DD, NB>(ix, ws, st);
   FPB_DISPATCH_D_NBITS(ix, CALL)
 #undef CALL

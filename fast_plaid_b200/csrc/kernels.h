@@ -18,15 +18,24 @@ struct Ws {
   int32_t* rerank() const { return reinterpret_cast<int32_t*>(base + L->off_rerank); }
   float* rerank_approx() const { return reinterpret_cast<float*>(base + L->off_rerank_approx); }
   float* exact() const { return reinterpret_cast<float*>(base + L->off_exact); }
+  uint32_t* cbitmap() const { return reinterpret_cast<uint32_t*>(base + L->off_cbitmap); }
+  int32_t* clist() const { return reinterpret_cast<int32_t*>(base + L->off_clist); }
+  int32_t* n_clist() const { return reinterpret_cast<int32_t*>(base + L->off_n_clist); }
+  uint32_t* sbitmap() const { return reinterpret_cast<uint32_t*>(base + L->off_sbitmap); }
 };
 
 int launch_pad_queries(const fpb_index* ix, const Ws& ws, const __half* d_queries, cudaStream_t st);
 int launch_centroid_scores(const fpb_index* ix, const Ws& ws, cudaStream_t st);   // K1
-int launch_probe(const fpb_index* ix, const Ws& ws, cudaStream_t st);             // K1b
-int launch_candidates(const fpb_index* ix, const Ws& ws, cudaStream_t st);        // K2
+int launch_probe(const fpb_index* ix, const Ws& ws, bool subset, cudaStream_t st);       // K1b
+int launch_candidates(const fpb_index* ix, const Ws& ws, bool subset, cudaStream_t st);  // K2
+int launch_subset(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const int64_t* d_offsets,
+                  int64_t max_len, cudaStream_t st);                                      // subset structures
+int launch_compact(const uint32_t* bitmap, const uint32_t* mask, int words, int32_t* out, int cap, int32_t* n_out,
+                   int B, cudaStream_t st);
 int launch_approx(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3
 int launch_select(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3b
-int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K5
+int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K5 (dispatch)
+int launch_maxsim_v2(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v2 (128/4)
 int launch_rank(const fpb_index* ix, const Ws& ws, int top_k, int64_t* d_out_ids, float* d_out_scores,
                 int32_t* d_out_counts, cudaStream_t st);                          // K6
 int launch_emit_records(const fpb_index* ix, const Ws& ws, fpb_record* d_records, cudaStream_t st);

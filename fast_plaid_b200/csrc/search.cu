@@ -39,11 +39,15 @@ int prepare(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws, 
     if (_rc != FPB_OK) return _rc; \
   } while (0)
 
-int run_until_maxsim(const fpb_index* ix, const Ws& ws, const __half* d_queries, cudaStream_t st) {
+int run_until_maxsim(const fpb_index* ix, const Ws& ws, const __half* d_queries, cudaStream_t st,
+                     const int32_t* d_subset_ids = nullptr, const int64_t* d_subset_offsets = nullptr,
+                     int64_t max_subset_len = 0) {
+  const bool subset = d_subset_ids != nullptr || d_subset_offsets != nullptr;
   FPB_TRY(launch_pad_queries(ix, ws, d_queries, st));
   FPB_TRY(launch_centroid_scores(ix, ws, st));
-  FPB_TRY(launch_probe(ix, ws, st));
-  FPB_TRY(launch_candidates(ix, ws, st));
+  if (subset) FPB_TRY(launch_subset(ix, ws, d_subset_ids, d_subset_offsets, max_subset_len, st));
+  FPB_TRY(launch_probe(ix, ws, subset, st));
+  FPB_TRY(launch_candidates(ix, ws, subset, st));
   FPB_TRY(launch_approx(ix, ws, st));
   FPB_TRY(launch_select(ix, ws, st));
   FPB_TRY(launch_maxsim(ix, ws, st));
@@ -64,6 +68,29 @@ extern "C" int fpb_search_batch(const fpb_index* ix, const void* d_queries, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Ws ws{&L, static_cast<char*>(d_ws)};
   FPB_TRY(run_until_maxsim(ix, ws, static_cast<const __half*>(d_queries), st));
+  FPB_TRY(launch_rank(ix, ws, p->top_k, d_out_ids, d_out_scores, d_out_counts, st));
+  return FPB_OK;
+}
+
+extern "C" int fpb_search_batch_subset(const fpb_index* ix, const void* d_queries, int B, int Q,
+                                       const fpb_params* p, const int32_t* d_subset_ids,
+                                       const int64_t* d_subset_offsets, int64_t max_subset_len, void* d_ws,
+                                       size_t ws_bytes, int64_t* d_out_ids, float* d_out_scores,
+                                       int32_t* d_out_counts, void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, true));
+  if (!d_queries || !d_out_ids || !d_out_scores || !d_out_counts || !d_subset_offsets) {
+    fpb_set_error("fpb_search_batch_subset: NULL query, subset-offset or output pointer");
+    return FPB_ERR_INVALID;
+  }
+  if (!(p->flags & FPB_FLAG_SUBSET)) {
+    fpb_set_error("fpb_search_batch_subset: params->flags must contain FPB_FLAG_SUBSET");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  FPB_TRY(run_until_maxsim(ix, ws, static_cast<const __half*>(d_queries), st, d_subset_ids, d_subset_offsets,
+                           max_subset_len));
   FPB_TRY(launch_rank(ix, ws, p->top_k, d_out_ids, d_out_scores, d_out_counts, st));
   return FPB_OK;
 }
@@ -124,15 +151,25 @@ extern "C" int fpb_stage_centroid_scores(const fpb_index* ix, const void* d_quer
   FPB_TRY(launch_pad_queries(ix, ws, static_cast<const __half*>(d_queries), st));
   return launch_centroid_scores(ix, ws, st);
 }
+extern "C" int fpb_stage_subset(const fpb_index* ix, const int32_t* d_subset_ids, const int64_t* d_subset_offsets,
+                                int64_t max_subset_len, int B, int Q, const fpb_params* p, void* d_ws,
+                                size_t ws_bytes, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  if (!d_subset_offsets || !(p->flags & FPB_FLAG_SUBSET)) {
+    fpb_set_error("fpb_stage_subset: NULL offsets or FPB_FLAG_SUBSET not set");
+    return FPB_ERR_INVALID;
+  }
+  return launch_subset(ix, ws, d_subset_ids, d_subset_offsets, max_subset_len, st);
+}
 extern "C" int fpb_stage_probe(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
                                size_t ws_bytes, void* stream) {
   FPB_STAGE_PROLOGUE(false)
-  return launch_probe(ix, ws, st);
+  return launch_probe(ix, ws, (p->flags & FPB_FLAG_SUBSET) != 0, st);
 }
 extern "C" int fpb_stage_candidates(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
                                     size_t ws_bytes, void* stream) {
   FPB_STAGE_PROLOGUE(true)
-  return launch_candidates(ix, ws, st);
+  return launch_candidates(ix, ws, (p->flags & FPB_FLAG_SUBSET) != 0, st);
 }
 extern "C" int fpb_stage_approx(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
                                 size_t ws_bytes, void* stream) {

@@ -40,7 +40,11 @@ class FpbParams(ctypes.Structure):
         ("n_full_scores", ctypes.c_int32),
         ("top_k", ctypes.c_int32),
         ("batch_size", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
     ]
+
+
+FPB_FLAG_SUBSET = 1
 
 
 class FpbLayout(ctypes.Structure):
@@ -54,6 +58,8 @@ class FpbLayout(ctypes.Structure):
         ("n_probe", ctypes.c_int32),
         ("cand_cap", ctypes.c_int32),
         ("bitmap_words", ctypes.c_int32),
+        ("cbitmap_words", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
         ("off_queries", ctypes.c_int64),
         ("off_S", ctypes.c_int64),
         ("off_tmax", ctypes.c_int64),
@@ -67,6 +73,10 @@ class FpbLayout(ctypes.Structure):
         ("off_rerank", ctypes.c_int64),
         ("off_rerank_approx", ctypes.c_int64),
         ("off_exact", ctypes.c_int64),
+        ("off_cbitmap", ctypes.c_int64),
+        ("off_clist", ctypes.c_int64),
+        ("off_n_clist", ctypes.c_int64),
+        ("off_sbitmap", ctypes.c_int64),
     ]
 
 
@@ -78,8 +88,10 @@ EXPORTED_SYMBOLS = [
     "fpb_index_destroy",
     "fpb_workspace_layout",
     "fpb_search_batch",
+    "fpb_search_batch_subset",
     "fpb_search_batch_host",
     "fpb_stage_centroid_scores",
+    "fpb_stage_subset",
     "fpb_stage_probe",
     "fpb_stage_candidates",
     "fpb_stage_approx",
@@ -124,6 +136,11 @@ def load_library() -> ctypes.CDLL:
         lib.fpb_workspace_layout.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), ctypes.POINTER(FpbLayout)]
         lib.fpb_search_batch.restype = i32
         lib.fpb_search_batch.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp, vp, vp]
+        lib.fpb_search_batch_subset.restype = i32
+        lib.fpb_search_batch_subset.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, vp, i64, vp, sz,
+                                                vp, vp, vp, vp]
+        lib.fpb_stage_subset.restype = i32
+        lib.fpb_stage_subset.argtypes = [vp, vp, vp, i64, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
         lib.fpb_search_batch_host.restype = i32
         lib.fpb_search_batch_host.argtypes = [
             vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp, vp, vp, vp, vp, vp, vp,
@@ -317,8 +334,9 @@ class DeviceIndex:
 
     # -- helpers -------------------------------------------------------------------------
     @staticmethod
-    def make_params(top_k: int, n_full_scores: int, n_ivf_probe: int, batch_size: int = 2000) -> FpbParams:
-        return FpbParams(int(n_ivf_probe), int(n_full_scores), int(top_k), int(batch_size))
+    def make_params(top_k: int, n_full_scores: int, n_ivf_probe: int, batch_size: int = 2000,
+                    flags: int = 0) -> FpbParams:
+        return FpbParams(int(n_ivf_probe), int(n_full_scores), int(top_k), int(batch_size), int(flags))
 
     def layout(self, B: int, Q: int, params: FpbParams) -> FpbLayout:
         lay = FpbLayout()
@@ -327,7 +345,7 @@ class DeviceIndex:
 
     def workspace(self, B: int, Q: int, params: FpbParams) -> tuple[torch.Tensor, FpbLayout]:
         """One grow-only device buffer per index, carved up by fpb_workspace_layout."""
-        key = (B, Q, params.n_ivf_probe, params.n_full_scores, params.top_k)
+        key = (B, Q, params.n_ivf_probe, params.n_full_scores, params.top_k, params.flags)
         with self._lock:
             lay = self._ws.get(key)
             if lay is None:
@@ -351,11 +369,22 @@ class DeviceIndex:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # -- search --------------------------------------------------------------------------
+    def _subset_csr(self, subset: list[list[int]], s: int, e: int) -> tuple[torch.Tensor, torch.Tensor, int]:
+        lens = [len(x) for x in subset[s:e]]
+        offs = torch.zeros(len(lens) + 1, dtype=torch.int64)
+        offs[1:] = torch.tensor(lens, dtype=torch.int64).cumsum(0)
+        flat = [i for x in subset[s:e] for i in x]
+        ids = torch.tensor(flat if flat else [0], dtype=torch.int64)
+        ids = ids.clamp(-1, 2**31 - 1).to(torch.int32)
+        return ids.to(self.device), offs.to(self.device), (max(lens) if lens else 0)
+
     def search(
-        self, queries: torch.Tensor, params: FpbParams
+        self, queries: torch.Tensor, params: FpbParams, subset: list[list[int]] | None = None
     ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """queries: fp16 [B, Q, D] on this device.  Returns device tensors
-        (ids int64 [B, top_k], scores f32 [B, top_k], counts int32 [B]).  Asynchronous."""
+        (ids int64 [B, top_k], scores f32 [B, top_k], counts int32 [B]).  Asynchronous.
+        `subset`: per query a list of GLOBAL doc ids to restrict the search to
+        (search.rs:494-517, :544-547)."""
         if queries.dim() != 3:
             raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries.shape)}")
         if queries.dtype != torch.float16 or queries.device != self.device:
@@ -370,18 +399,34 @@ class DeviceIndex:
         counts = torch.empty((B,), dtype=torch.int32, device=self.device)
         if B == 0:
             return ids, scores, counts
+        if subset is not None:
+            if len(subset) != B:
+                raise ValueError("Subset length must match number of queries.")
+            params = FpbParams(params.n_ivf_probe, params.n_full_scores, params.top_k, params.batch_size,
+                               params.flags | FPB_FLAG_SUBSET)
         step = self.max_queries_per_call(Q, params)
         with torch.cuda.device(self.device):
             for s in range(0, B, step):
                 e = min(B, s + step)
                 buf, lay = self.workspace(e - s, Q, params)
-                _check(
-                    self._lib.fpb_search_batch(
-                        self._handle, queries[s:e].data_ptr(), e - s, Q, ctypes.byref(params), buf.data_ptr(),
-                        buf.numel(), ids[s:e].data_ptr(), scores[s:e].data_ptr(), counts[s:e].data_ptr(),
-                        self._stream(),
+                if subset is None:
+                    _check(
+                        self._lib.fpb_search_batch(
+                            self._handle, queries[s:e].data_ptr(), e - s, Q, ctypes.byref(params), buf.data_ptr(),
+                            buf.numel(), ids[s:e].data_ptr(), scores[s:e].data_ptr(), counts[s:e].data_ptr(),
+                            self._stream(),
+                        )
                     )
-                )
+                else:
+                    sid, soff, smax = self._subset_csr(subset, s, e)
+                    _check(
+                        self._lib.fpb_search_batch_subset(
+                            self._handle, queries[s:e].data_ptr(), e - s, Q, ctypes.byref(params), sid.data_ptr(),
+                            soff.data_ptr(), smax, buf.data_ptr(), buf.numel(), ids[s:e].data_ptr(),
+                            scores[s:e].data_ptr(), counts[s:e].data_ptr(), self._stream(),
+                        )
+                    )
+                    self._keepalive = (sid, soff)  # until the stream has consumed them
         return ids, scores, counts
 
     def search_host(
@@ -466,9 +511,14 @@ class DeviceIndex:
         return ids, scores, counts
 
     # -- stage-level access for the parity tests and the roofline bench -------------------
-    def run_stages(self, queries: torch.Tensor, params: FpbParams, upto: str = "rank") -> dict[str, Any]:
+    def run_stages(self, queries: torch.Tensor, params: FpbParams, upto: str = "rank",
+                   subset: list[list[int]] | None = None) -> dict[str, Any]:
         """Run the pipeline stage by stage and return views of every intermediate."""
         order = ["centroid_scores", "probe", "candidates", "approx", "select", "maxsim", "rank"]
+        if subset is not None:
+            params = FpbParams(params.n_ivf_probe, params.n_full_scores, params.top_k, params.batch_size,
+                               params.flags | FPB_FLAG_SUBSET)
+            order.insert(1, "subset")
         queries = queries.contiguous()
         B, Q, _ = queries.shape
         buf, lay = self.workspace(B, Q, params)
@@ -480,6 +530,11 @@ class DeviceIndex:
                 if name == "centroid_scores":
                     _check(self._lib.fpb_stage_centroid_scores(self._handle, queries.data_ptr(), B, Q, p,
                                                                buf.data_ptr(), buf.numel(), st))
+                elif name == "subset":
+                    sid, soff, smax = self._subset_csr(subset, 0, B)
+                    _check(self._lib.fpb_stage_subset(self._handle, sid.data_ptr(), soff.data_ptr(), smax, B, Q, p,
+                                                      buf.data_ptr(), buf.numel(), st))
+                    torch.cuda.synchronize(self.device)
                 elif name == "rank":
                     k = params.top_k
                     ids = torch.empty((B, k), dtype=torch.int64, device=self.device)

@@ -398,12 +398,19 @@ class FastPlaid:
                 raise ValueError("Subset length must match number of queries.")
         return search_indices, queries_embeddings, subset
 
-    def _search_device(self, idx: DeviceIndex, queries: torch.Tensor, params) -> list[list[tuple[int, float]]]:
+    def _search_device(self, idx: DeviceIndex, queries: torch.Tensor, params,
+                       subset: list[list[int]] | None = None) -> list[list[tuple[int, float]]]:
         """search_on_device (fast_plaid.py:188-253) for the whole batch."""
         if queries.dim() != 3:
             raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries.shape)}")
         if self.shard is not None:
+            if subset is not None:
+                raise NotImplementedError("subset= with a document-sharded index is not supported yet")
             return self._search_sharded(idx, queries, params)
+        if subset is not None:
+            q16 = queries.to(torch.float16).to(idx.device)
+            ids, scores, counts = idx.search(q16, params, subset=subset)
+            return _results_to_lists(ids.cpu(), scores.cpu(), counts.cpu())
         if queries.device.type == "cuda":
             q16 = queries.to(device=idx.device, dtype=torch.float16)  # fast_plaid.py:241
             ids, scores, counts = idx.search(q16, params)
@@ -444,21 +451,18 @@ class FastPlaid:
         """Search the index (fast_plaid.py:930-983).  Returns, per query, up to ``top_k``
         ``(doc_id, score)`` pairs in rank order."""
         search_indices, queries, subset = self._prepare_search(queries_embeddings, subset)
-        if subset is not None:
-            raise NotImplementedError(
-                "subset= filtering is not wired into the B200 engine yet (SURVEY.md 8f-4)."
-            )
         params = DeviceIndex.make_params(top_k, n_full_scores, n_ivf_probe, batch_size)
         if len(self.devices) == 1:
-            return self._search_device(search_indices[self.devices[0]], queries, params)
+            return self._search_device(search_indices[self.devices[0]], queries, params, subset)
         # several devices in ONE process: replicated index, query list split across devices
         # (the reference's multi-GPU mode, fast_plaid.py:893-928)
         n = len(self.devices)
         chunk = math.ceil(queries.shape[0] / n)
         chunks = list(torch.split(queries, chunk))
+        sub_chunks = [None] * len(chunks) if subset is None else [subset[i : i + chunk] for i in range(0, len(subset), chunk)]
         with ThreadPoolExecutor(max_workers=n) as ex:
             futs = [
-                ex.submit(self._search_device, search_indices[d], chunks[i], params)
+                ex.submit(self._search_device, search_indices[d], chunks[i], params, sub_chunks[i])
                 for i, d in enumerate(self.devices)
                 if i < len(chunks)
             ]

@@ -77,7 +77,11 @@ typedef struct fpb_params {
   int32_t n_full_scores; /* search.rs:179, default 4096 */
   int32_t top_k;         /* search.rs:182               */
   int32_t batch_size;    /* search.rs:176, ignored      */
+  int32_t flags;         /* FPB_FLAG_*                  */
 } fpb_params;
+
+/* The workspace carries the per-query subset structures (search.rs:494-517, :544-547). */
+#define FPB_FLAG_SUBSET 1
 
 /* Byte offsets of every intermediate inside the workspace, so the parity tests can read
  * each stage (S, probed cells, candidates, approx scores, rerank list, exact scores)
@@ -85,6 +89,7 @@ typedef struct fpb_params {
 typedef struct fpb_layout {
   int64_t total_bytes;
   int32_t B, Q, Qp, n_tiles, R, n_probe, cand_cap, bitmap_words;
+  int32_t cbitmap_words, reserved0;
   int64_t off_queries;   /* f16 [B, Qp, D]  zero-padded queries                       */
   int64_t off_S;         /* f16 [B, K, Qp]  centroid scores          (search.rs:491)  */
   int64_t off_tmax;      /* f16 [B, Qp, n_tiles] per-128-centroid-tile column maxima  */
@@ -98,6 +103,11 @@ typedef struct fpb_layout {
   int64_t off_rerank;    /* i32 [B, R] doc ids, (approx desc, id asc) (search.rs:602-619) */
   int64_t off_rerank_approx; /* f32 [B, R]                                            */
   int64_t off_exact;     /* f32 [B, R]                               (search.rs:651-656) */
+  /* only with FPB_FLAG_SUBSET (otherwise zero-sized): */
+  int64_t off_cbitmap;   /* u32 [B, cbitmap_words] centroids present in the subset docs (search.rs:496-503) */
+  int64_t off_clist;     /* i32 [B, K] the same as a sorted list                      */
+  int64_t off_n_clist;   /* i32 [B]                                                   */
+  int64_t off_sbitmap;   /* u32 [B, bitmap_words] the subset's documents              */
 } fpb_layout;
 
 /* Workspace sizing for a batch of B queries of Q tokens. */
@@ -119,6 +129,19 @@ int fpb_search_batch(const fpb_index* index, const void* d_queries, int B, int Q
                      int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts,
                      void* stream);
 
+/* Search restricted, per query, to a subset of documents (`subset=` of FastPlaid.search,
+ * search.rs:494-517 + :544-547): probing is limited to the centroids that occur in the subset's
+ * documents and the candidate set is intersected with the subset.
+ *   d_subset_ids      i32 [total]  GLOBAL doc ids, query b owns [offsets[b], offsets[b+1])
+ *   d_subset_offsets  i64 [B+1]
+ *   max_subset_len    the largest per-query subset length (grid sizing)
+ * params->flags must contain FPB_FLAG_SUBSET (it sizes the workspace). */
+int fpb_search_batch_subset(const fpb_index* index, const void* d_queries, int B, int Q,
+                            const fpb_params* params, const int32_t* d_subset_ids,
+                            const int64_t* d_subset_offsets, int64_t max_subset_len, void* d_workspace,
+                            size_t workspace_bytes, int64_t* d_out_ids, float* d_out_scores,
+                            int32_t* d_out_counts, void* stream);
+
 /* Same call with HOST buffers: H2D of the queries, the search, D2H of the results and a
  * stream synchronise all happen inside.  d_out_* are device scratch of the same shapes. */
 int fpb_search_batch_host(const fpb_index* index, const void* h_queries, int B, int Q,
@@ -131,6 +154,9 @@ int fpb_search_batch_host(const fpb_index* index, const void* h_queries, int B, 
  * search.rs on the workspace laid out by fpb_workspace_layout. ---- */
 int fpb_stage_centroid_scores(const fpb_index*, const void* d_queries, int B, int Q,
                               const fpb_params*, void* d_workspace, size_t, void* stream); /* search.rs:491 */
+int fpb_stage_subset(const fpb_index*, const int32_t* d_subset_ids, const int64_t* d_subset_offsets,
+                     int64_t max_subset_len, int B, int Q, const fpb_params*, void* d_workspace, size_t,
+                     void* stream); /* search.rs:496-503: run between centroid_scores and probe */
 int fpb_stage_probe(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,
                     size_t, void* stream); /* search.rs:520-532 */
 int fpb_stage_candidates(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace,

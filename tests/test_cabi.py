@@ -29,13 +29,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(engine.EXPORTED_SYMBOLS) == declared, "engine.EXPORTED_SYMBOLS is out of sync with the header"
-    assert lib.fpb_abi_version() == 1
+    assert lib.fpb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
-    assert ctypes.sizeof(engine.FpbParams) == 16
-    # 1 int64 + 8 int32 + 13 int64
-    assert ctypes.sizeof(engine.FpbLayout) == 8 + 8 * 4 + 13 * 8
+    assert ctypes.sizeof(engine.FpbParams) == 20
+    # 1 int64 + 10 int32 + 17 int64
+    assert ctypes.sizeof(engine.FpbLayout) == 8 + 10 * 4 + 17 * 8
 
 
 def test_errors_are_reported_not_thrown():

@@ -84,6 +84,12 @@ def test_fastplaid_surface_on_gpu(tmp_path, cuda_device):
     # list-of-tensors input is zero padded like the reference (fast_plaid.py:772-780)
     res_list = fp.search([queries[0][:20], queries[1]], top_k=5)
     assert len(res_list) == 2 and all(len(r) == 5 for r in res_list)
+    # subset filtering through the public surface (tests/test.py:409-435): single list and per-query lists
+    sub = list(range(0, 300, 3))
+    r_sub = fp.search(queries[:4], top_k=5, subset=sub)
+    assert all(d in set(sub) for r in r_sub for d, _ in r) and all(len(r) == 5 for r in r_sub)
+    r_sub2 = fp.search(queries[:2], top_k=5, subset=[[1, 2, 3], [10]])
+    assert [len(r) for r in r_sub2] == [3, 1] and r_sub2[1][0][0] == 10
     # top_k beyond the index size (tests/test.py:880-886)
     big = fp.search(queries[:2], top_k=1000)
     assert all(0 < len(r) <= 300 for r in big)

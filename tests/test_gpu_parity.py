@@ -219,3 +219,50 @@ def test_compress_only_index_refuses_search(cuda_device):
     d = DeviceIndex(t, cuda_device)
     with pytest.raises(ValueError, match="compress_only"):
         d.search(queries.half().to(cuda_device), params)
+
+
+@pytest.mark.parametrize("name", ["base", "dim64", "ragged_short"])
+def test_subset_search_matches_oracle(name, cuda_device):
+    """`subset=` (search.rs:494-517, :544-547): restricted probing + candidate intersection."""
+    oidx, didx, queries, params, st = _setup(name, cuda_device)
+    B, Q = queries.shape[0], queries.shape[1]
+    n_docs = int(oidx.doc_lengths.shape[0])
+    g = torch.Generator().manual_seed(5)
+    subsets = []
+    for b in range(B):
+        kind = b % 5
+        if kind == 0:
+            sub = torch.randperm(n_docs, generator=g)[: max(1, n_docs // 10)].tolist()
+        elif kind == 1:
+            sub = [int(torch.randint(0, n_docs, (1,), generator=g))]
+        elif kind == 2:
+            sub = []
+        elif kind == 3:
+            sub = list(range(n_docs))
+        else:
+            sub = torch.randint(0, n_docs, (50,), generator=g).tolist() * 2  # duplicates
+        subsets.append(sub)
+    stg = didx.run_stages(queries.half().to(cuda_device), params, subset=subsets)
+    torch.cuda.synchronize()
+    for b in range(B):
+        S_b = stg["S"][b, :, :Q].cpu().contiguous()
+        ref = po.search_one(queries[b], oidx, params.n_ivf_probe, 2000, params.n_full_scores, params.top_k,
+                            subset=torch.tensor(subsets[b], dtype=torch.int64), ties="canonical", return_stages=True,
+                            inject={"S": S_b})
+        cells = torch.unique(stg["cells"][b].cpu().flatten().long())
+        assert torch.equal(cells[cells >= 0], ref["cells"]), f"query {b}: probed cells differ"
+        n = int(stg["n_cand"][b])
+        assert torch.equal(stg["cand"][b, :n].cpu().long(), ref["candidates"]), f"query {b}: candidates differ"
+        cnt = int(stg["counts"][b])
+        got = stg["ids"][b, :cnt].cpu().tolist()
+        assert set(got) <= set(subsets[b])  # tests/test.py:409-411
+        assert cnt == min(params.top_k, len(ref["ids"]))
+        if cnt:
+            sc = dict(zip(ref["ids"], ref["scores"]))
+            ok, why = ranking_consistent(got, stg["scores"][b, :cnt].cpu().tolist(), sc, 1e-3,
+                                         fallback=lambda d, b=b: float(oracle_exact_scores(oidx, queries[b], [d])[0]))
+            assert ok, why
+    # the one-call entry point agrees with the staged run
+    ids, scores, counts = didx.search(queries.half().to(cuda_device), params, subset=subsets)
+    torch.cuda.synchronize()
+    assert torch.equal(ids, stg["ids"]) and torch.equal(counts, stg["counts"])
