@@ -224,7 +224,11 @@ def run_b200(args) -> dict:
     counts = torch.empty((B,), dtype=torch.int32, device=device)
     rec = torch.empty((B, lay.R, 16), dtype=torch.uint8, device=device)
     gathered = torch.empty((world, B, lay.R, 16), dtype=torch.uint8, device=device)
+    keys = torch.empty((B, lay.R), dtype=torch.int64, device=device)
+    all_keys = torch.empty((world, B, lay.R), dtype=torch.int64, device=device)
     stage_names = ["centroid_scores", "probe", "candidates", "approx", "select", "maxsim", "final"]
+    if world > 1:
+        stage_names = ["centroid_scores", "probe", "candidates", "approx", "select", "exchange_keys", "maxsim", "final"]
 
     def one_step(qb: torch.Tensor, events: list | None) -> None:
         def mark():
@@ -244,6 +248,15 @@ def run_b200(args) -> dict:
         mark()
         _check(lib.fpb_stage_select(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), st))
         mark()
+        if world > 1:
+            # two-step sharded search: global pruning threshold before the exact stage
+            import torch.distributed as dist
+
+            _check(lib.fpb_stage_keys(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), keys.data_ptr(), st))
+            dist.all_gather_into_tensor(all_keys.view(-1), keys.view(-1))
+            _check(lib.fpb_shard_apply_threshold(didx._handle, all_keys.data_ptr(), world, rank, B, Q, pp,
+                                                 buf.data_ptr(), buf.numel(), st))
+            mark()
         _check(lib.fpb_stage_maxsim(didx._handle, B, Q, pp, buf.data_ptr(), buf.numel(), st))
         mark()
         if world == 1:
@@ -301,7 +314,9 @@ def run_b200(args) -> dict:
         import torch.distributed as dist
 
         qd = q16.pin_memory().to(device, non_blocking=True)
-        r = didx.search_records(qd, params)
+        kk = didx.shard_approx_keys(qd, params)
+        dist.all_gather_into_tensor(all_keys.view(-1), kk.view(-1))
+        r = didx.shard_exact_records(all_keys, rank, Q, params)
         dist.all_gather_into_tensor(gathered.view(-1), r.view(-1))
         i2, s2, c2 = didx.merge_records(gathered, k)
         return _results_to_lists(i2.cpu(), s2.cpu(), c2.cpu())
@@ -325,7 +340,9 @@ def run_b200(args) -> dict:
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
 
     peak, peak_src = measured_peak_hbm()
-    ms_time = stage_ms[5] / 1000.0
+    i_ms = stage_names.index("maxsim")
+    i_ap = stage_names.index("approx")
+    ms_time = stage_ms[i_ms] / 1000.0
     achieved = ms_bytes / ms_time / 1e9 if ms_time > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -355,7 +372,7 @@ def run_b200(args) -> dict:
         "config": {
             "workload": f"{args.config}: {cfg['desc']}",
             "n_ivf_probe": N_IVF_PROBE, "n_full_scores": N_FULL, "reranked_per_query": lay.R,
-            "parallelism": f"document shards x{world}" + (" + NCCL all-gather of per-shard records" if world > 1 else ""),
+            "parallelism": f"document shards x{world}" + (" + 2 NCCL all-gathers (approx keys, then records of the globally surviving docs)" if world > 1 else ""),
             "l2": "inputs larger than L2: 20 GB index, 1.07 GB score table per batch; "
                   f"{N_QUERY_BATCHES} distinct query batches rotate across steps",
             "candidates_per_query_mean": n_cand_mean,
@@ -365,16 +382,16 @@ def run_b200(args) -> dict:
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "fp32 host queries -> fp16 cast on host -> fpb_search_batch_host (H2D, search, D2H, sync) -> "
                         "Python list[list[(doc_id, score)]]"},
-        "gpu_launches": (10 if world == 1 else 11) * args.steps,
+        "gpu_launches": (10 if world == 1 else 13) * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "k5_maxsim_kernel (fused residual decompression + MaxSim)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": stage_ms[5]},
+                     "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": stage_ms[i_ms]},
         "stages_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
         "approx_stage": {"hbm_bytes_per_launch": ap_hbm, "l2_gather_bytes_per_launch": ap_gather,
-                         "hbm_gbs": ap_hbm / (stage_ms[3] / 1000.0) / 1e9 if stage_ms[3] > 0 else None,
-                         "l2_gather_gbs": ap_gather / (stage_ms[3] / 1000.0) / 1e9 if stage_ms[3] > 0 else None},
+                         "hbm_gbs": ap_hbm / (stage_ms[i_ap] / 1000.0) / 1e9 if stage_ms[i_ap] > 0 else None,
+                         "l2_gather_gbs": ap_gather / (stage_ms[i_ap] / 1000.0) / 1e9 if stage_ms[i_ap] > 0 else None},
         "wall_s_timed_region": round(t_wall, 3),
     }
 

@@ -41,11 +41,15 @@ k2_compact_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restric
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int w0 = 0; w0 < bitmap_words; w0 += 1024) {
-    const int wi = w0 + tid;
-    uint32_t w = (wi < bitmap_words) ? bm[wi] : 0u;
-    if (mk && wi < bitmap_words) w &= mk[wi];
-    const int c = __popc(w);
+  for (int w0 = 0; w0 < bitmap_words; w0 += 4096) {
+    const int wi = w0 + tid * 4;  // 4 consecutive words per thread keeps the output ordered
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      w[u] = (wi + u < bitmap_words) ? bm[wi + u] : 0u;
+      if (mk && wi + u < bitmap_words) w[u] &= mk[wi + u];
+    }
+    const int c = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
     int incl = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -67,10 +71,14 @@ k2_compact_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restric
     __syncthreads();
     const int base = s_base;
     int pos = base + warp_sums[warp] + incl - c;
-    while (w) {
-      const int bit = __ffs(w) - 1;
-      w &= w - 1;
-      out[pos++] = wi * 32 + bit;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint32_t x = w[u];
+      while (x) {
+        const int bit = __ffs(x) - 1;
+        x &= x - 1;
+        out[pos++] = (wi + u) * 32 + bit;
+      }
     }
     __syncthreads();
     if (tid == 1023) s_base = base + warp_sums[31] + incl;  // total of this round

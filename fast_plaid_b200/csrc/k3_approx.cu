@@ -9,6 +9,8 @@
 // rows (one L1 wavefront per row instead of four), and the running maxima stay in registers.
 // The stage is bound by L2 gather bandwidth (Qp*2 bytes per token per query); the codes
 // stream from HBM once per (query, candidate).
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace {
@@ -28,8 +30,8 @@ __global__ void k3_prefix_kernel(const int32_t* __restrict__ n_cand, int B, int3
   }
 }
 
-template <int LPR>
-__global__ void __launch_bounds__(K3_THREADS)
+template <int LPR, int UNROLL, int MINB>
+__global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
                  const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
                  const int32_t* __restrict__ n_cand, int32_t* __restrict__ work, int B,
@@ -72,18 +74,25 @@ k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* 
       const int64_t o0 = doc_offsets[d];
       const int len = int(doc_offsets[d + 1] - o0);
       __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
-      for (int base = 0; base < len; base += 32) {
-        const int t = base + lane;
-        const int code = (t < len) ? __ldg(codes + o0 + t) : -1;
+      for (int base = 0; base < len; base += 32 * UNROLL) {
+        int code[UNROLL];
 #pragma unroll
-        for (int j = 0; j < LPR; ++j) {
-          const int c = __shfl_sync(0xffffffffu, code, j * TPI + grp);
-          if (c >= 0) {
-            const uint4 v = __ldg(Sb + int64_t(c) * LPR + sub);
-            m0 = __hmax2(m0, u32_as_half2(v.x));
-            m1 = __hmax2(m1, u32_as_half2(v.y));
-            m2 = __hmax2(m2, u32_as_half2(v.z));
-            m3 = __hmax2(m3, u32_as_half2(v.w));
+        for (int u = 0; u < UNROLL; ++u) {
+          const int t = base + u * 32 + lane;
+          code[u] = (t < len) ? __ldg(codes + o0 + t) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+          for (int j = 0; j < LPR; ++j) {
+            const int c = __shfl_sync(0xffffffffu, code[u], j * TPI + grp);
+            if (c >= 0) {
+              const uint4 v = __ldg(Sb + int64_t(c) * LPR + sub);
+              m0 = __hmax2(m0, u32_as_half2(v.x));
+              m1 = __hmax2(m1, u32_as_half2(v.y));
+              m2 = __hmax2(m2, u32_as_half2(v.z));
+              m3 = __hmax2(m3, u32_as_half2(v.w));
+            }
           }
         }
       }
@@ -123,13 +132,19 @@ __device__ __forceinline__ uint64_t approx_key(float a, uint32_t i) {
   return (uint64_t(f32_key(a)) << 32) | uint64_t(0xffffffffu - i);
 }
 
+// Digits of the 64-bit key, most significant first: 11+11+10 bits cover the score, the rest
+// only matters when scores tie at the threshold.
+__constant__ int K3B_LO[6] = {53, 42, 32, 21, 10, 0};
+__constant__ int K3B_W[6] = {11, 11, 10, 11, 11, 10};
+constexpr int K3B_VPT = 4;  // independent loads in flight per thread
+
 __global__ void __launch_bounds__(1024)
 k3b_select_kernel(const float* __restrict__ approx, const int32_t* __restrict__ cand, int cand_cap,
                   const int32_t* __restrict__ n_cand, int n_dec, int Rp2, int32_t* __restrict__ rerank,
                   float* __restrict__ rerank_approx, int32_t* __restrict__ n_rerank) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-  __shared__ int hist[256];
+  __shared__ int hist[2048];
   __shared__ int s_need, s_hd, s_cnt;
   __shared__ uint64_t s_prefix, s_mask;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -151,34 +166,62 @@ k3b_select_kernel(const float* __restrict__ approx, const int32_t* __restrict__ 
     s_prefix = 0;
     s_mask = 0;
   }
-  const int n_up = (n + 1023) & ~1023;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    if (tid < 256) hist[tid] = 0;
+  const int stride = 1024 * K3B_VPT;
+  const int n_up = (n + stride - 1) / stride * stride;
+  for (int pass = 0; pass < 6; ++pass) {
+    const int lo = K3B_LO[pass], width = K3B_W[pass];
+    const uint64_t dmask = (1ull << width) - 1ull;
+    for (int i = tid; i < 2048; i += 1024) hist[i] = 0;
     __syncthreads();
     const uint64_t prefix = s_prefix, mask = s_mask;
-    for (int i = tid; i < n_up; i += 1024) {
-      const bool valid = i < n;
-      const uint64_t key = valid ? approx_key(ab[i], uint32_t(i)) : 0ull;
-      const bool in = valid && ((key & mask) == prefix);
-      const unsigned act = __ballot_sync(0xffffffffu, in);
-      if (in) {
-        const int bin = int((key >> shift) & 255ull);
-        const unsigned peers = __match_any_sync(act, bin);
-        if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    for (int i0 = tid; i0 < n_up; i0 += stride) {
+      float v[K3B_VPT];
+#pragma unroll
+      for (int u = 0; u < K3B_VPT; ++u) {
+        const int i = i0 + u * 1024;
+        v[u] = (i < n) ? ab[i] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < K3B_VPT; ++u) {
+        const int i = i0 + u * 1024;
+        const bool valid = i < n;
+        const uint64_t key = valid ? approx_key(v[u], uint32_t(i)) : 0ull;
+        const bool in = valid && ((key & mask) == prefix);
+        const unsigned act = __ballot_sync(0xffffffffu, in);
+        if (in) {
+          const int bin = int((key >> lo) & dmask);
+          const unsigned peers = __match_any_sync(act, bin);
+          if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+        }
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      int need = s_need, cum = 0, d = 255;
-      for (; d > 0; --d) {
-        const int h = hist[d];
-        if (cum + h >= need) break;
-        cum += h;
+    if (tid < 32) {
+      // warp 0: find the digit d with  count(digit > d) < need <= count(digit >= d)
+      const int nbins = 1 << width;
+      const int per = nbins / 32;  // bins per lane, lane 31 owns the top bins
+      int mine = 0;
+      for (int k = 0; k < per; ++k) mine += hist[lane * per + k];
+      // suffix sums over lanes (lanes above me)
+      int above = 0;
+      for (int l = 31; l >= 0; --l) {
+        const int c = __shfl_sync(0xffffffffu, mine, l);
+        if (l > lane) above += c;
       }
-      s_need = need - cum;
-      s_hd = hist[d];
-      s_prefix = prefix | (uint64_t(d) << shift);
-      s_mask = mask | (255ull << shift);
+      const int need = s_need;
+      const bool here = (above < need) && (above + mine >= need);
+      if (here) {
+        int cum = above, d = lane * per + per - 1;
+        for (; d > lane * per; --d) {
+          const int h = hist[d];
+          if (cum + h >= need) break;
+          cum += h;
+        }
+        s_need = need - cum;
+        s_hd = hist[d];
+        s_prefix = prefix | (uint64_t(d) << lo);
+        s_mask = mask | (dmask << lo);
+      }
     }
     __syncthreads();
     if (s_hd == s_need) break;  // the whole bucket is selected
@@ -186,11 +229,23 @@ k3b_select_kernel(const float* __restrict__ approx, const int32_t* __restrict__ 
   const uint64_t T = s_prefix;  // unprocessed low bits are zero
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += 1024) {
-    const uint64_t key = approx_key(ab[i], uint32_t(i));
-    if (key >= T) {
-      const int pos = atomicAdd(&s_cnt, 1);
-      if (pos < Rp2) keys[pos] = key;
+  for (int i0 = tid; i0 < n_up; i0 += stride) {
+    float v[K3B_VPT];
+#pragma unroll
+    for (int u = 0; u < K3B_VPT; ++u) {
+      const int i = i0 + u * 1024;
+      v[u] = (i < n) ? ab[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < K3B_VPT; ++u) {
+      const int i = i0 + u * 1024;
+      if (i < n) {
+        const uint64_t key = approx_key(v[u], uint32_t(i));
+        if (key >= T) {
+          const int pos = atomicAdd(&s_cnt, 1);
+          if (pos < Rp2) keys[pos] = key;
+        }
+      }
     }
   }
   __syncthreads();
@@ -225,9 +280,21 @@ template <int LPR>
 int launch_k3_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   const int blocks = ix->sm_count * 8;
-  k3_approx_kernel<LPR><<<blocks, K3_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes,
-                                                       ws.cand(), L.cand_cap, ws.n_cand(), ws.work(), L.B,
-                                                       ws.approx());
+  // FPB_K3_VARIANT selects a tuning variant (A/B measurements; all compute identical values)
+  static const int variant = getenv("FPB_K3_VARIANT") ? atoi(getenv("FPB_K3_VARIANT")) : 0;
+#define K3_LAUNCH(U, M)                                                                                     \
+  k3_approx_kernel<LPR, U, M><<<blocks, K3_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets,            \
+                                                             ix->doc_codes, ws.cand(), L.cand_cap, ws.n_cand(), \
+                                                             ws.work(), L.B, ws.approx())
+  // measured on cfg-3 (ms): U1/M6 26.2, U2/M6 20.4, U1/M8 23.5, U2/M8 20.8, U4/M4 22.4
+  switch (variant) {
+    case 1: K3_LAUNCH(1, 6); break;
+    case 2: K3_LAUNCH(2, 7); break;
+    case 3: K3_LAUNCH(3, 5); break;
+    case 4: K3_LAUNCH(3, 6); break;
+    default: K3_LAUNCH(2, 6); break;
+  }
+#undef K3_LAUNCH
   FPB_LAUNCH_CHECK("k3_approx");
   return FPB_OK;
 }

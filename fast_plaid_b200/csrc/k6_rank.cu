@@ -156,7 +156,131 @@ k6_merge_kernel(const fpb_record* __restrict__ all, int n_shards, int B, int R, 
   if (tid == 0) out_counts[b] = cnt;
 }
 
+// two-step sharded search, step 1: 64-bit keys of the local pruned list
+__global__ void emit_keys_kernel(const float* __restrict__ rerank_approx, const int32_t* __restrict__ rerank,
+                                 const int32_t* __restrict__ n_rerank, int B, int R, int64_t doc_id_base,
+                                 uint64_t* __restrict__ keys) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= int64_t(B) * R) return;
+  const int b = int(i / R), r = int(i % R);
+  uint64_t k = 0;
+  if (r < n_rerank[b])
+    k = (uint64_t(f32_key(rerank_approx[i])) << 32) | uint64_t(0xffffffffu - uint32_t(doc_id_base + rerank[i]));
+  keys[i] = k;
+}
+
+// step 2: global R-th best key per query; the local list keeps (in order) the entries at or above
+// it.  One CTA per query.
+__global__ void __launch_bounds__(1024)
+apply_threshold_kernel(const uint64_t* __restrict__ all, int n_shards, int rank, int B, int R, int P,
+                       int32_t* __restrict__ n_rerank, int32_t* __restrict__ rerank,
+                       float* __restrict__ rerank_approx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  __shared__ int warp_sums[32];
+  __shared__ int s_base;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = n_shards * R;
+  for (int i = tid; i < P; i += 1024) {
+    uint64_t k = 0;
+    if (i < total) k = all[(int64_t(i / R) * B + b) * R + (i % R)];
+    keys[i] = k;
+  }
+  __syncthreads();
+  bitonic_desc(keys, P, tid, 1024);
+  const uint64_t T = keys[R - 1];  // 0 when the whole index has fewer than R candidates
+  // ordered compaction of the local list (it is in id order when nothing was pruned locally):
+  // thread t owns entries [t*PER, (t+1)*PER), one block-wide exclusive scan gives the positions
+  const uint64_t* mine = all + (int64_t(rank) * B + b) * R;
+  int32_t* rr = rerank + int64_t(b) * R;
+  float* ra = rerank_approx + int64_t(b) * R;
+  int32_t* tmp_id = reinterpret_cast<int32_t*>(keys);   // reuse the sort buffer (P*8 >= R*8 bytes)
+  float* tmp_ap = reinterpret_cast<float*>(tmp_id + R);
+  const int n_old = n_rerank[b];
+  constexpr int PER = 4;  // R <= 4096
+  int32_t id[PER];
+  float ap[PER];
+  bool keep[PER];
+  int c = 0;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int i = tid * PER + u;
+    keep[u] = false;
+    if (i < n_old && i < R) {
+      const uint64_t k = mine[i];
+      keep[u] = (k != 0) && (k >= T);
+      id[u] = rr[i];
+      ap[u] = ra[i];
+    }
+    c += keep[u] ? 1 : 0;
+  }
+  int incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();  // also: everybody has read T / keys[] before tmp_* overwrites the buffer
+  if (warp == 0) {
+    const int ws = warp_sums[lane];
+    int wincl = ws;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wincl, off);
+      if (lane >= off) wincl += v;
+    }
+    warp_sums[lane] = wincl - ws;
+    if (lane == 31) s_base = wincl;
+  }
+  __syncthreads();
+  int pos = warp_sums[warp] + incl - c;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    if (keep[u]) {
+      tmp_id[pos] = id[u];
+      tmp_ap[pos] = ap[u];
+      ++pos;
+    }
+  }
+  __syncthreads();
+  const int n_new = s_base;
+  for (int i = tid; i < n_new; i += 1024) {
+    rr[i] = tmp_id[i];
+    ra[i] = tmp_ap[i];
+  }
+  if (tid == 0) n_rerank[b] = n_new;
+}
+
 }  // namespace
+
+int launch_emit_keys(const fpb_index* ix, const Ws& ws, uint64_t* d_keys, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
+  const int64_t n = int64_t(L.B) * L.R;
+  emit_keys_kernel<<<int((n + 255) / 256), 256, 0, st>>>(ws.rerank_approx(), ws.rerank(), ws.n_rerank(), L.B, L.R,
+                                                        ix->doc_id_base, d_keys);
+  FPB_LAUNCH_CHECK("emit_keys");
+  return FPB_OK;
+}
+
+int launch_apply_threshold(const Ws& ws, const uint64_t* d_all_keys, int n_shards, int rank, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
+  const int P = fpb_next_pow2(n_shards * L.R);
+  const size_t smem = size_t(P) * 8;
+  if (smem > 200 * 1024) {
+    fpb_set_error("apply_threshold: n_shards*R=%d keys per query exceed the shared-memory sort", n_shards * L.R);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    FPB_CUDA_CHECK(cudaFuncSetAttribute(apply_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  apply_threshold_kernel<<<L.B, 1024, smem, st>>>(d_all_keys, n_shards, rank, L.B, L.R, P, ws.n_rerank(),
+                                                  ws.rerank(), ws.rerank_approx());
+  FPB_LAUNCH_CHECK("apply_threshold");
+  return FPB_OK;
+}
 
 int launch_rank(const fpb_index* ix, const Ws& ws, int top_k, int64_t* d_out_ids, float* d_out_scores,
                 int32_t* d_out_counts, cudaStream_t st) {

@@ -134,6 +134,53 @@ extern "C" int fpb_search_shard(const fpb_index* ix, const void* d_queries, int 
   return FPB_OK;
 }
 
+extern "C" int fpb_shard_approx_keys(const fpb_index* ix, const void* d_queries, int B, int Q,
+                                     const fpb_params* p, void* d_ws, size_t ws_bytes, uint64_t* d_keys,
+                                     void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, true));
+  if (!d_queries || !d_keys) {
+    fpb_set_error("fpb_shard_approx_keys: NULL query or key pointer");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  FPB_TRY(launch_pad_queries(ix, ws, static_cast<const __half*>(d_queries), st));
+  FPB_TRY(launch_centroid_scores(ix, ws, st));
+  FPB_TRY(launch_probe(ix, ws, false, st));
+  FPB_TRY(launch_candidates(ix, ws, false, st));
+  FPB_TRY(launch_approx(ix, ws, st));
+  FPB_TRY(launch_select(ix, ws, st));
+  return launch_emit_keys(ix, ws, d_keys, st);
+}
+
+extern "C" int fpb_shard_apply_threshold(const fpb_index* ix, const uint64_t* d_all_keys, int n_shards,
+                                         int shard_rank, int B, int Q, const fpb_params* p, void* d_ws,
+                                         size_t ws_bytes, void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, false));
+  if (!d_all_keys || n_shards < 1 || shard_rank < 0 || shard_rank >= n_shards) {
+    fpb_set_error("fpb_shard_apply_threshold: bad arguments");
+    return FPB_ERR_INVALID;
+  }
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  return launch_apply_threshold(ws, d_all_keys, n_shards, shard_rank, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fpb_shard_exact_records(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                                       size_t ws_bytes, fpb_record* d_records, void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, false));
+  if (!d_records) {
+    fpb_set_error("fpb_shard_exact_records: NULL record pointer");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  FPB_TRY(launch_maxsim(ix, ws, st));
+  return launch_emit_records(ix, ws, d_records, st);
+}
+
 // ---- stage-level entry points ----------------------------------------------------------
 #define FPB_STAGE_PROLOGUE(need_ivf)                                   \
   fpb_layout L;                                                        \
@@ -204,4 +251,13 @@ extern "C" int fpb_stage_records(const fpb_index* ix, int B, int Q, const fpb_pa
     return FPB_ERR_INVALID;
   }
   return launch_emit_records(ix, ws, d_records, st);
+}
+extern "C" int fpb_stage_keys(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws, size_t ws_bytes,
+                              uint64_t* d_keys, void* stream) {
+  FPB_STAGE_PROLOGUE(false)
+  if (!d_keys) {
+    fpb_set_error("fpb_stage_keys: NULL key pointer");
+    return FPB_ERR_INVALID;
+  }
+  return launch_emit_keys(ix, ws, d_keys, st);
 }

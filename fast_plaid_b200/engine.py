@@ -98,9 +98,13 @@ EXPORTED_SYMBOLS = [
     "fpb_stage_select",
     "fpb_stage_maxsim",
     "fpb_stage_rank",
+    "fpb_stage_keys",
     "fpb_stage_records",
     "fpb_search_shard",
     "fpb_merge_shards",
+    "fpb_shard_approx_keys",
+    "fpb_shard_apply_threshold",
+    "fpb_shard_exact_records",
     "fpb_reconstruct",
     "fpb_token_scores",
 ]
@@ -154,10 +158,18 @@ def load_library() -> ctypes.CDLL:
             fn.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
         lib.fpb_stage_rank.restype = i32
         lib.fpb_stage_rank.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp, vp, vp]
+        lib.fpb_stage_keys.restype = i32
+        lib.fpb_stage_keys.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
         lib.fpb_stage_records.restype = i32
         lib.fpb_stage_records.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
         lib.fpb_search_shard.restype = i32
         lib.fpb_search_shard.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
+        lib.fpb_shard_approx_keys.restype = i32
+        lib.fpb_shard_approx_keys.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
+        lib.fpb_shard_apply_threshold.restype = i32
+        lib.fpb_shard_apply_threshold.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
+        lib.fpb_shard_exact_records.restype = i32
+        lib.fpb_shard_exact_records.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
         lib.fpb_merge_shards.restype = i32
         lib.fpb_merge_shards.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
         lib.fpb_reconstruct.restype = i32
@@ -491,6 +503,31 @@ class DeviceIndex:
                     rec.data_ptr(), self._stream(),
                 )
             )
+        return rec
+
+    # two-step sharded search (exact-scores only the globally surviving documents)
+    def shard_approx_keys(self, queries: torch.Tensor, params: FpbParams) -> torch.Tensor:
+        queries = queries.contiguous()
+        B, Q, _ = queries.shape
+        buf, lay = self.workspace(B, Q, params)
+        keys = torch.empty((B, lay.R), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self._lib.fpb_shard_approx_keys(self._handle, queries.data_ptr(), B, Q, ctypes.byref(params),
+                                                   buf.data_ptr(), buf.numel(), keys.data_ptr(), self._stream()))
+        return keys
+
+    def shard_exact_records(self, all_keys: torch.Tensor, rank: int, Q: int, params: FpbParams) -> torch.Tensor:
+        """all_keys: int64 [n_shards, B, R] (all-gathered).  Applies the global pruning threshold to
+        this shard's list, exact-scores the survivors, returns uint8 [B, R, 16] records."""
+        n_shards, B, R = all_keys.shape
+        buf, lay = self.workspace(B, Q, params)
+        rec = torch.empty((B, R, 16), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self._lib.fpb_shard_apply_threshold(self._handle, all_keys.contiguous().data_ptr(), n_shards, rank,
+                                                       B, Q, ctypes.byref(params), buf.data_ptr(), buf.numel(),
+                                                       self._stream()))
+            _check(self._lib.fpb_shard_exact_records(self._handle, B, Q, ctypes.byref(params), buf.data_ptr(),
+                                                     buf.numel(), rec.data_ptr(), self._stream()))
         return rec
 
     def merge_records(

@@ -426,8 +426,16 @@ class FastPlaid:
         import torch.distributed as dist
 
         q16 = queries.to(device=idx.device, dtype=torch.float16, non_blocking=True)
-        rec = idx.search_records(q16, params)
-        world = self.shard[1]
+        rank, world = self.shard
+        # step 1: local pruning, all-gather of the approximate-score keys
+        keys = idx.shard_approx_keys(q16, params)
+        all_keys = torch.empty((world,) + tuple(keys.shape), dtype=torch.int64, device=idx.device)
+        if world > 1:
+            dist.all_gather_into_tensor(all_keys.view(-1), keys.view(-1))
+        else:
+            all_keys.copy_(keys.unsqueeze(0))
+        # step 2: exact scores of the globally surviving documents only, all-gather of the records
+        rec = idx.shard_exact_records(all_keys, rank, int(q16.shape[1]), params)
         gathered = torch.empty((world,) + tuple(rec.shape), dtype=torch.uint8, device=idx.device)
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(-1), rec.view(-1))

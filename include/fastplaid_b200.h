@@ -171,6 +171,8 @@ int fpb_stage_rank(const fpb_index*, int B, int Q, const fpb_params*, void* d_wo
                    size_t, int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts,
                    void* stream); /* search.rs:659-666 */
 
+int fpb_stage_keys(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace, size_t,
+                   uint64_t* d_keys, void* stream); /* sharded two-step mode: emit [B, R] approx keys */
 int fpb_stage_records(const fpb_index*, int B, int Q, const fpb_params*, void* d_workspace, size_t,
                       struct fpb_record* d_records, void* stream); /* sharded mode: emit [B, R] records */
 
@@ -192,6 +194,23 @@ int fpb_search_shard(const fpb_index* index, const void* d_queries, int B, int Q
 int fpb_merge_shards(const fpb_record* d_all_records /* [n_shards, B, R] */, int n_shards,
                      int B, int R, int top_k, int64_t* d_out_ids, float* d_out_scores,
                      int32_t* d_out_counts, void* stream);
+
+/* Two-step variant (exact-scores only the documents that survive the GLOBAL pruning, so the
+ * MaxSim work divides by the number of shards):
+ *   1. fpb_shard_approx_keys : stages up to the local pruning; emits [B, R] 64-bit keys
+ *                              (approx score, then smaller global id first; 0 = padding)
+ *   2. all-gather of the keys; fpb_shard_apply_threshold finds, per query, the R-th best key of
+ *      the whole index and shrinks this shard's re-rank list to the entries at or above it
+ *   3. fpb_shard_exact_records : MaxSim on the shrunk lists, emits [B, R] fpb_record
+ *   4. all-gather of the records; fpb_merge_shards ranks them. */
+int fpb_shard_approx_keys(const fpb_index* index, const void* d_queries, int B, int Q,
+                          const fpb_params* params, void* d_workspace, size_t workspace_bytes,
+                          uint64_t* d_keys /* [B, R] */, void* stream);
+int fpb_shard_apply_threshold(const fpb_index* index, const uint64_t* d_all_keys /* [n_shards, B, R] */,
+                              int n_shards, int shard_rank, int B, int Q, const fpb_params* params,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
+int fpb_shard_exact_records(const fpb_index* index, int B, int Q, const fpb_params* params,
+                            void* d_workspace, size_t workspace_bytes, fpb_record* d_records, void* stream);
 
 /* ---- by-products of the MaxSim kernel ("next" rows of SURVEY.md 8f-3) ---- */
 /* reconstruct_embeddings (rust/utils/embeddings.rs:12-69): decompressed, normalised

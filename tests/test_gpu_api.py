@@ -143,3 +143,13 @@ def test_two_shards_on_one_gpu_equal_the_unsharded_search(cuda_device):
             assert torch.equal(c2, counts)
             assert torch.equal(i2, ids), f"world={world} n_full={n_full}"
             assert torch.equal(s2, scores)
+            # two-step variant: keys -> global threshold -> exact scores of the survivors only
+            shards = [DeviceIndex(*shard_tensors(t, r, world)[:1], cuda_device, doc_id_base=shard_tensors(t, r, world)[1])
+                      for r in range(world)]
+            all_keys = torch.stack([d.shard_approx_keys(queries, params) for d in shards])
+            recs2 = [d.shard_exact_records(all_keys, r, int(queries.shape[1]), params) for r, d in enumerate(shards)]
+            n_scored = sum(int((rec.view(torch.int64).view(rec.shape[0], rec.shape[1], 2)[:, :, 1] >= 0).sum()) for rec in recs2)
+            i3, s3, c3 = whole.merge_records(torch.stack(recs2), top_k)
+            torch.cuda.synchronize()
+            assert torch.equal(i3, ids) and torch.equal(s3, scores) and torch.equal(c3, counts)
+            assert n_scored <= queries.shape[0] * (n_full // 4)  # exact-scored docs: at most R per query in total

@@ -53,6 +53,15 @@ def _worker(rank: int, world: int, port: int, out):
         i2, s2, c2 = mine.merge_records(gathered, top_k)
         torch.cuda.synchronize()
         ok = ok and torch.equal(i2, ids) and torch.equal(s2, scores) and torch.equal(c2, counts)
+        # two-step variant
+        keys = mine.shard_approx_keys(queries, params)
+        all_keys = torch.empty((world,) + tuple(keys.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_keys.view(-1), keys.view(-1))
+        rec2 = mine.shard_exact_records(all_keys, rank, int(queries.shape[1]), params)
+        dist.all_gather_into_tensor(gathered.view(-1), rec2.view(-1))
+        i3, s3, c3 = mine.merge_records(gathered, top_k)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(i3, ids) and torch.equal(s3, scores) and torch.equal(c3, counts)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
