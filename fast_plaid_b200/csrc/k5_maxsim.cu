@@ -359,9 +359,17 @@ int launch_k5_q(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
 }  // namespace
 
 int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
-  // FPB_K5_V1=1 forces the generic v1 kernel (A/B measurements); both are bit-identical.
-  static const bool force_v1 = getenv("FPB_K5_V1") != nullptr;
-  if (!force_v1) {
+  // FPB_K5 = v1 | v2 | v3 pins one implementation (A/B measurements; all are bit-identical).
+  // Default: v3 (tcgen05) where it applies, then v2, then the generic v1.
+  static const char* pin = getenv("FPB_K5");
+  const bool allow_v3 = !pin || pin[1] == '3';
+  const bool allow_v2 = !pin || pin[1] == '2';
+  if (allow_v3) {
+    bool handled = false;
+    const int rc = launch_maxsim_v3(ix, ws, st, &handled);
+    if (rc != FPB_OK || handled) return rc;
+  }
+  if (allow_v2) {
     bool handled = false;
     const int rc = launch_maxsim_v2(ix, ws, st, &handled);
     if (rc != FPB_OK || handled) return rc;
