@@ -25,11 +25,10 @@
 namespace {
 
 constexpr int V3_THREADS = 512;
-constexpr int V3_DECODE_WARPS = 11;
 constexpr int V3_MMA_WARP = 11;
 constexpr int V3_EPI_WARP0 = 12;
 constexpr int V3_STAGES = 3;
-constexpr int V3_TILE_N = 128;       // tokens per tile
+constexpr int V3_TILE_N = 128;       // accumulator slot width in TMEM columns (tiles hold <= 112 tokens)
 constexpr int V3_MAX_TILES = 256;    // tiles per chunk (host picks docs per chunk accordingly)
 constexpr int V3_MAX_DOCS = 32;
 constexpr int V3_KBLOCK_BYTES = 128 * 128;        // 128 rows x 128 B (64 fp16) per K block
@@ -150,7 +149,7 @@ struct DocMeta {
 __global__ void __launch_bounds__(V3_THREADS, 1)
 k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ doc_offsets,
                     const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals, WPerm wp,
-                    const __half* __restrict__ Qpad, int Q, int Qp, int B, int R, int docs_per_chunk,
+                    const __half* __restrict__ Qpad, int Q, int Qp, int B, int R, int docs_per_chunk, int n_dec,
                     const int32_t* __restrict__ n_rerank, const int32_t* __restrict__ rerank,
                     float* __restrict__ exact, int* __restrict__ counter) {
   extern __shared__ unsigned char smem_dyn[];
@@ -172,6 +171,12 @@ k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_epi_warps = (Qp + 31) / 32;
+  // decode slots: warps 0..10 plus the epilogue warps this query length leaves idle; pass s of every
+  // tile belongs to slot s, so a tile holds n_dec passes = 8*n_dec tokens
+  const int dec_slot = (warp < V3_MMA_WARP) ? warp
+                       : (warp >= V3_EPI_WARP0 + n_epi_warps ? V3_MMA_WARP + (warp - V3_EPI_WARP0 - n_epi_warps) : -1);
+  const bool is_decoder = dec_slot >= 0 && dec_slot < n_dec;
+  const int tile_tokens = 8 * n_dec;
 
   // ---- one-time setup ----
   for (int i = tid; i < 256 * 32; i += V3_THREADS) {
@@ -182,7 +187,7 @@ k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
     reinterpret_cast<uint4*>(smA)[i] = make_uint4(0u, 0u, 0u, 0u);  // query rows >= Qp stay zero
   if (tid == 0) {
     for (int s = 0; s < V3_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, V3_DECODE_WARPS);
+      mbar_init(bar_full + 8 * s, n_dec);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int t = 0; t < 2; ++t) {
@@ -232,10 +237,10 @@ k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
         int nt = 0, np = 0;
         for (int i = 0; i < nd; ++i) {
           const int len = docs[i].len;
-          for (int t0 = 0; t0 < len; t0 += V3_TILE_N) {
+          for (int t0 = 0; t0 < len; t0 += tile_tokens) {
             tiles[nt].doc = i;
             tiles[nt].tok0 = t0;
-            tiles[nt].nvalid = min(V3_TILE_N, len - t0);
+            tiles[nt].nvalid = min(tile_tokens, len - t0);
             tiles[nt].pass0 = np;
             np += (tiles[nt].nvalid + 7) >> 3;
             ++nt;
@@ -260,44 +265,51 @@ k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
     const int n_tiles = misc[1];
     const int n_docs = misc[2];
 
-    if (warp < V3_DECODE_WARPS) {
+    if (is_decoder) {
       // =========================== decode warps ===========================
       const int j = lane & 3, tslot = lane >> 2;
       const int prow = (tslot >> 1) + 4 * (tslot & 1);
       const uint32_t lut_lane = smem_u32(lut) + lane * 4;
-      // cursor over this warp's passes: (T, p); pass index in the chunk gp = tiles[T].pass0 + p, gp % 11 == warp
-      auto first_in_tile = [&](int T) {
-        const int m = tiles[T].pass0 % V3_DECODE_WARPS;
-        return (warp - m + V3_DECODE_WARPS) % V3_DECODE_WARPS;
+      const int p = dec_slot;  // this warp's pass inside every tile
+      auto has_pass = [&](int T) { return p * 8 < tiles[T].nvalid; };
+      auto next_tile = [&](int T) {  // first tile >= T where this slot has a pass
+        while (T < n_tiles && !has_pass(T)) ++T;
+        return T;
       };
-      auto advance = [&](int& T, int& p) {  // next pass of this warp at or after (T, p); T == n_tiles when none
-        while (T < n_tiles) {
-          const int np = (tiles[T].nvalid + 7) >> 3;
-          if (p < np) return;
-          ++T;
-          if (T < n_tiles) p = first_in_tile(T);
-        }
-      };
-      auto issue_loads = [&](int T, int p, Raw3& raw) {
+      // software pipeline: codes are fetched two tiles ahead, residual + centroid rows one tile ahead
+      auto tok_of = [&](int T, int64_t& row) {
         const TileMeta tm = tiles[T];
         const DocMeta dm = docs[tm.doc];
-        const int tok = min(tm.tok0 + p * 8 + prow, dm.len - 1);
-        const int code = __ldg(codes + dm.o0 + tok);
-        v3_load_raw(raw, residuals, C, dm.o0 + tok, code, j);
+        row = dm.o0 + min(tm.tok0 + p * 8 + prow, dm.len - 1);
       };
 
-      int T = 0, p = (n_tiles > 0) ? first_in_tile(0) : 0;
-      advance(T, p);
+      int T = next_tile(0);
+      int T1 = (T < n_tiles) ? next_tile(T + 1) : n_tiles;
       int done = 0;  // tiles [0, done) have received this warp's arrival
+      int64_t row_cur = 0, row_1 = 0;
+      int code_1 = 0;
       Raw3 cur;
-      if (T < n_tiles) issue_loads(T, p, cur);
+      if (T < n_tiles) {
+        tok_of(T, row_cur);
+        const int code_0 = __ldg(codes + row_cur);
+        if (T1 < n_tiles) {
+          tok_of(T1, row_1);
+          code_1 = __ldg(codes + row_1);
+        }
+        v3_load_raw(cur, residuals, C, row_cur, code_0, j);
+      }
       while (T < n_tiles) {
-        int Tn = T, pn = p + V3_DECODE_WARPS;
-        advance(Tn, pn);
+        const int T2 = (T1 < n_tiles) ? next_tile(T1 + 1) : n_tiles;
+        int64_t row_2 = 0;
+        int code_2 = 0;
+        if (T2 < n_tiles) {
+          tok_of(T2, row_2);
+          code_2 = __ldg(codes + row_2);
+        }
         Raw3 nxt;
-        if (Tn < n_tiles) issue_loads(Tn, pn, nxt);
+        if (T1 < n_tiles) v3_load_raw(nxt, residuals, C, row_1, code_1, j);
 
-        // tiles without a pass of this warp still need its arrival, in order
+        // tiles without a pass of this slot still need its arrival, in order
         while (done < T) {
           const uint32_t g = gtile + done;
           mbar_wait(bar_empty + 8 * (g % V3_STAGES), ((g / V3_STAGES) & 1) ^ 1);
@@ -306,7 +318,7 @@ k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
         }
         const uint32_t g = gtile + T;
         const uint32_t stage = g % V3_STAGES;
-        mbar_wait(bar_empty + 8 * stage, ((g / V3_STAGES) & 1) ^ 1);  // returns at once after the first pass of a tile
+        mbar_wait(bar_empty + 8 * stage, ((g / V3_STAGES) & 1) ^ 1);
 
         // ---- decode: e = fp16(w_perm[nibble] + centroid), n = fp16(sqrt(sum e^2)), e_hat = fp16(e / n) ----
         __half2 e[16];
@@ -345,15 +357,14 @@ k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
           const int c = j + 4 * k, kb = c >> 3, cc = c & 7;
           *reinterpret_cast<uint4*>(st + kb * V3_KBLOCK_BYTES + ((cc ^ prow) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        // last pass of this warp in tile T -> publish
-        if (Tn != T) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-          done = T + 1;
-        }
-        T = Tn;
-        p = pn;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        done = T + 1;
+        T = T1;
+        T1 = T2;
+        row_1 = row_2;
+        code_1 = code_2;
         cur = nxt;
       }
       while (done < n_tiles) {
@@ -386,7 +397,7 @@ k5_maxsim_v3_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
         }
       }
       __syncwarp();
-    } else if (warp - V3_EPI_WARP0 < n_epi_warps) {
+    } else if (warp >= V3_EPI_WARP0 && warp - V3_EPI_WARP0 < n_epi_warps) {
       // =========================== epilogue ===========================
       const int ew = warp - V3_EPI_WARP0;
       const int q = ew * 32 + lane;
@@ -459,7 +470,10 @@ int launch_maxsim_v3(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* h
   *handled = false;
   const fpb_layout& L = *ws.L;
   if (ix->dim != 128 || ix->nbits != 4 || L.Qp > 128) return FPB_OK;
-  const int64_t tiles_per_doc = (ix->max_doc_len + V3_TILE_N - 1) / V3_TILE_N;
+  const int n_epi = (L.Qp + 31) / 32;
+  const int n_dec = (11 + (4 - n_epi)) & ~1;  // decode slots (even, so a tile is a multiple of 16 tokens): 14/12/12/10
+  const int tile_tokens = 8 * n_dec;
+  const int64_t tiles_per_doc = (ix->max_doc_len + tile_tokens - 1) / tile_tokens;
   if (tiles_per_doc < 1 || tiles_per_doc > V3_MAX_TILES) return FPB_OK;
   int docs_per_chunk = int(V3_MAX_TILES / tiles_per_doc);
   if (docs_per_chunk > V3_MAX_DOCS) docs_per_chunk = V3_MAX_DOCS;
@@ -477,7 +491,7 @@ int launch_maxsim_v3(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* h
   const int blocks = chunks < ix->sm_count ? chunks : ix->sm_count;
   k5_maxsim_v3_kernel<<<blocks, V3_THREADS, V3Smem::bytes, st>>>(
       ix->centroids, ix->doc_offsets, ix->doc_codes, ix->doc_residuals, wp, ws.queries(), L.Q, L.Qp, L.B, L.R,
-      docs_per_chunk, ws.n_rerank(), ws.rerank(), ws.exact(), counter);
+      docs_per_chunk, n_dec, ws.n_rerank(), ws.rerank(), ws.exact(), counter);
   FPB_LAUNCH_CHECK("k5_maxsim_v3");
   return FPB_OK;
 }
