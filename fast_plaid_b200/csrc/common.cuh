@@ -30,6 +30,10 @@ struct fpb_index {
   // w_perm[i] = bucket_weights[bitrev_nbits(i)]  (closed form of the two LUTs of
   // residual_codec.rs:83-140): element j of a byte is w_perm[(byte >> (8-nbits*(j+1))) & mask]
   uint16_t w_perm_bits[16];
+  // TMA descriptor of the centroid table: 2-D [K, dim] fp16, box 64 x 128, SWIZZLE_128B
+  // (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint; has_tmap = 0 if unavailable)
+  alignas(64) unsigned char tmap_centroids[128];
+  int has_tmap;
 };
 
 struct WPerm {

@@ -3,7 +3,39 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
+
+// The driver-API entry point is resolved at run time (no link against libcuda).
+typedef CUresult (*fpb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static int make_centroid_tmap(fpb_index* ix) {
+  ix->has_tmap = 0;
+  if (ix->dim != 128) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(ix->tmap_centroids);
+  const cuuint64_t gdim[2] = {cuuint64_t(ix->dim), cuuint64_t(ix->K)};
+  const cuuint64_t gstride[1] = {cuuint64_t(ix->dim) * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = reinterpret_cast<fpb_encode_tiled_fn>(fn)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ix->centroids), gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) ix->has_tmap = 1;
+  return 0;
+}
 
 static thread_local char g_err[512] = "";
 
@@ -97,6 +129,7 @@ extern "C" int fpb_index_create(fpb_index** out, int device, int nbits, int dim,
     }
   }
   ix->E = n_tokens;
+  make_centroid_tmap(ix);
   *out = ix;
   return FPB_OK;
 }

@@ -8,6 +8,8 @@
 // as the reference does.  The epilogue writes S in the [b][k][q] layout the approximate stage
 // gathers from (one contiguous Qp*2-byte row per centroid and query) and, per 128-row tile,
 // the column maxima that let K1b find the top-n cells by touching ~n tiles instead of all K.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace {
@@ -303,6 +305,13 @@ int launch_pad_queries(const fpb_index* ix, const Ws& ws, const __half* d_querie
 }
 
 int launch_centroid_scores(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+  // FPB_K1=v1 pins the mma.sync kernel; default is the tcgen05 kernel where it applies.
+  static const char* pin = getenv("FPB_K1");
+  if (!pin || pin[1] != '1') {
+    bool handled = false;
+    const int rc = launch_centroid_scores_v2(ix, ws, st, &handled);
+    if (rc != FPB_OK || handled) return rc;
+  }
   switch (ix->dim) {
     case 64: return launch_k1_d<64>(ix, ws, st);
     case 128: return launch_k1_d<128>(ix, ws, st);
