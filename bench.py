@@ -484,21 +484,47 @@ def cpu_baseline(didx, queries_host: torch.Tensor, params, res_gpu, n_queries: i
     torch.cuda.synchronize()
     ids, scores, counts = ids.cpu(), scores.cpu(), counts.cpu()
     same_lists, overlap, max_rel = 0, 0.0, 0.0
+    valid_rankings, outside = 0, 0
     for i in range(n):
         r_ids, r_sc = ref[i]
         g = ids[i, : int(counts[i])].tolist()
+        gs = scores[i, : int(counts[i])].tolist()
         same_lists += int(g == r_ids)
         overlap += len(set(g) & set(r_ids)) / max(1, len(r_ids))
         sc_of = dict(zip(r_ids, r_sc))
-        for d, s in zip(g, scores[i, : int(counts[i])].tolist()):
-            if d in sc_of:
-                max_rel = max(max_rel, abs(s - sc_of[d]) / max(1.0, abs(sc_of[d])))
+        # reference exact score (search.rs:626-656) of every document the engine returned that the
+        # reference list does not hold: a valid result may differ at a near-tie of the k-th score
+        extra = [d for d in g if d not in sc_of]
+        outside += len(extra)
+        if extra:
+            sel = torch.tensor(extra, dtype=torch.int64)
+            codes, lens = po.ragged_lookup(oidx.doc_codes, oidx.doc_offsets, oidx.doc_lengths, sel)
+            res, _ = po.ragged_lookup(oidx.doc_residuals, oidx.doc_offsets, oidx.doc_lengths, sel)
+            emb = po.decompress_residuals(res, oidx.bucket_weights, oidx.byte_reversed_bits_map,
+                                          oidx.bucket_weight_indices_lookup, codes, oidx.centroids, oidx.dim, oidx.nbits)
+            padded, mask = po.direct_pad_sequences(emb, lens, 0.0)
+            ts = padded.matmul(q[i].half().unsqueeze(0).transpose(-2, -1))
+            for d, v in zip(extra, po.colbert_score_reduce(ts, mask).tolist()):
+                sc_of[d] = v
+        ok, prev = True, None
+        for d, s_ in zip(g, gs):
+            r_ = sc_of[d]
+            max_rel = max(max_rel, abs(s_ - r_) / max(1.0, abs(r_)))
+            if abs(s_ - r_) > 1e-3 * max(1.0, abs(r_)) or (prev is not None and r_ > prev + 1e-3 * max(1.0, abs(r_))):
+                ok = False
+            prev = r_
+        valid_rankings += int(ok)
     cb = {"value": n / dt, "unit": "queries/s", "cores": cores, "kind": "port",
           "sample": f"first {n} queries of the batch, full index, sequential queries, torch intra-op threads={cores} "
                     f"(fastest of {thread_timings} ms on a probe; host has {os.cpu_count()} logical cpus)",
           "seconds": round(dt, 2)}
     parity = {"queries": n, "identical_id_lists": same_lists, "mean_topk_overlap": overlap / n,
-              "max_rel_score_err_on_common_ids": max_rel}
+              "docs_outside_reference_list": outside,
+              "valid_rankings_of_reference_scores_within_1e-3": valid_rankings,
+              "max_rel_score_err": max_rel,
+              "note": "a returned ranking is valid if every returned doc carries the reference's exact score to "
+                      "1e-3 relative and no doc is ranked above one whose reference score is larger by more than "
+                      "that; docs outside the reference list arise from near-ties at the top_k / pruning boundaries"}
     return cb, parity
 
 
