@@ -372,6 +372,15 @@ class DeviceIndex:
             return self._buf, lay
 
     def max_queries_per_call(self, Q: int, params: FpbParams, budget_bytes: int = 6 << 30) -> int:
+        key = ("maxq", Q, params.n_ivf_probe, params.n_full_scores, params.top_k, params.flags, budget_bytes)
+        hit = self._ws.get(key)
+        if hit is not None:
+            return hit
+        val = self._max_queries_per_call(Q, params, budget_bytes)
+        self._ws[key] = val
+        return val
+
+    def _max_queries_per_call(self, Q: int, params: FpbParams, budget_bytes: int) -> int:
         one = self.layout(1, Q, params).total_bytes
         two = self.layout(2, Q, params).total_bytes
         per_q = max(1, two - one)
@@ -449,9 +458,8 @@ class DeviceIndex:
         synchronises the stream.  Returns HOST tensors (ids, scores, counts)."""
         if queries_host.dim() != 3:
             raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries_host.shape)}")
-        if queries_host.dtype != torch.float16 or queries_host.device.type != "cpu":
-            raise ValueError("search_host expects fp16 queries in host memory")
-        queries_host = queries_host.contiguous()
+        if queries_host.device.type != "cpu" or not queries_host.dtype.is_floating_point:
+            raise ValueError("search_host expects floating-point queries in host memory")
         B, Q, D = queries_host.shape
         if D != self.dim:
             raise ValueError(f"query dim {D} != index dim {self.dim}")
@@ -466,6 +474,7 @@ class DeviceIndex:
                     "d_ids": torch.empty((B, k), dtype=torch.int64, device=self.device),
                     "d_scores": torch.empty((B, k), dtype=torch.float32, device=self.device),
                     "d_counts": torch.empty((B,), dtype=torch.int32, device=self.device),
+                    "h_q": torch.empty((B, Q, D), dtype=torch.float16).pin_memory(),
                     "h_ids": torch.empty((B, k), dtype=torch.int64).pin_memory(),
                     "h_scores": torch.empty((B, k), dtype=torch.float32).pin_memory(),
                     "h_counts": torch.empty((B,), dtype=torch.int32).pin_memory(),
@@ -473,6 +482,9 @@ class DeviceIndex:
                 self._io[key] = io
         if B == 0:
             return io["h_ids"], io["h_scores"], io["h_counts"]
+        # one pass: cast to fp16 (fast_plaid.py:241 does the cast on the host too) into pinned memory
+        io["h_q"].copy_(queries_host)
+        queries_host = io["h_q"]
         step = self.max_queries_per_call(Q, params)
         with torch.cuda.device(self.device):
             for s in range(0, B, step):

@@ -415,10 +415,8 @@ class FastPlaid:
             q16 = queries.to(device=idx.device, dtype=torch.float16)  # fast_plaid.py:241
             ids, scores, counts = idx.search(q16, params)
             return _results_to_lists(ids.cpu(), scores.cpu(), counts.cpu())
-        q16 = queries.to(torch.float16)  # cast on the host like the reference (fast_plaid.py:241)
-        if not q16.is_pinned():
-            q16 = q16.contiguous().pin_memory()
-        ids, scores, counts = idx.search_host(q16, params)
+        # fp16 cast on the host like the reference (fast_plaid.py:241), straight into pinned staging
+        ids, scores, counts = idx.search_host(queries, params)
         return _results_to_lists(ids, scores, counts)
 
     def _search_sharded(self, idx: DeviceIndex, queries: torch.Tensor, params) -> list[list[tuple[int, float]]]:

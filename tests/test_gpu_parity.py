@@ -159,7 +159,7 @@ def test_end_to_end_against_reference_ties(name, cuda_device):
 
 def test_host_path_matches_device_path(cuda_device):
     oidx, didx, queries, params, st = _setup("base", cuda_device)
-    h_ids, h_scores, h_counts = didx.search_host(queries.half().pin_memory(), params)
+    h_ids, h_scores, h_counts = didx.search_host(queries, params)  # fp32 host queries
     assert torch.equal(h_ids, st["ids"].cpu())
     assert torch.equal(h_counts, st["counts"].cpu())
     assert torch.equal(h_scores, st["scores"].cpu())
@@ -266,3 +266,84 @@ def test_subset_search_matches_oracle(name, cuda_device):
     ids, scores, counts = didx.search(queries.half().to(cuda_device), params, subset=subsets)
     torch.cuda.synchronize()
     assert torch.equal(ids, stg["ids"]) and torch.equal(counts, stg["counts"])
+
+
+# ---- edge cases the reference's tests exercise (tests/test.py) plus size extremes ----------------
+def _search_vs_oracle(oidx, didx, queries, params, device, tol=1e-3):
+    ids, scores, counts = didx.search(queries.half().to(device), params)
+    torch.cuda.synchronize()
+    ids, scores, counts = ids.cpu(), scores.cpu(), counts.cpu()
+    for b in range(queries.shape[0]):
+        ref = po.search_one(queries[b], oidx, params.n_ivf_probe, 2000, params.n_full_scores, 10**9, ties="torch",
+                            return_stages=True)
+        n = int(counts[b])
+        assert n == min(params.top_k, len(ref["ids"])), (n, len(ref["ids"]))
+        ok, why = ranking_consistent(ids[b, :n].tolist(), scores[b, :n].tolist(), dict(zip(ref["ids"], ref["scores"])), tol,
+                                     fallback=lambda d, b=b: float(oracle_exact_scores(oidx, queries[b], [d])[0]))
+        assert ok, f"query {b}: {why}"
+    return ids, scores, counts
+
+
+def test_unnormalised_randn_inputs_like_the_reference_tests(cuda_device):
+    """tests/test.py feeds raw torch.randn documents and queries (norm ~ 11), dim 128 and 64."""
+    from fast_plaid_b200.engine import DeviceIndex
+
+    for dim in (128, 64):
+        docs = make_docs(150, 20, 60, dim=dim, seed=3, normalize=False)
+        oidx, _ = build_oracle_index(docs, kmeans_niters=2)
+        g = torch.Generator().manual_seed(4)
+        queries = torch.randn(3, 30, dim, generator=g)
+        didx = DeviceIndex(to_index_tensors(oidx), cuda_device)
+        for n_probe in (2, 16):  # tests/test.py:897-906
+            _search_vs_oracle(oidx, didx, queries, DeviceIndex.make_params(10, 4096, n_probe), cuda_device, tol=2e-3)
+
+
+def test_tiny_index_and_single_token_query(cuda_device):
+    """K < 128 (one partial centroid tile), B = 1, Q = 1 (padded to 16 internally)."""
+    from fast_plaid_b200.engine import DeviceIndex
+
+    docs = make_docs(12, 3, 6, seed=8)
+    oidx, _ = build_oracle_index(docs, kmeans_niters=2)
+    assert oidx.centroids.shape[0] < 128
+    didx = DeviceIndex(to_index_tensors(oidx), cuda_device)
+    q = make_queries(1, 1, seed=9, docs=docs)
+    ids, scores, counts = _search_vs_oracle(oidx, didx, q, DeviceIndex.make_params(5, 4096, 8), cuda_device)
+    assert 0 < int(counts[0]) <= 5
+
+
+def test_large_rerank_budget_and_top_k(cuda_device):
+    """n_full_scores = 16384 -> 4096 re-ranked documents (the supported maximum), top_k = 3000."""
+    from fast_plaid_b200.engine import DeviceIndex
+
+    oidx, didx, queries, _, _ = _setup("base", cuda_device)
+    params = DeviceIndex.make_params(3000, 16384, 8)
+    ids, scores, counts = _search_vs_oracle(oidx, didx, queries[:2], params, cuda_device)
+    assert int(counts.max()) <= 1000  # the index holds 1000 documents
+    with pytest.raises(ValueError):
+        didx.search(queries[:1].half().to(cuda_device), DeviceIndex.make_params(10, 4 * 4097, 8))
+
+
+def test_empty_document_gets_the_reference_score(cuda_device):
+    """A zero-token document scores Q * fp16(-9999) = Q * -10000 (search.rs:395) and never wins."""
+    from fast_plaid_b200.engine import DeviceIndex, IndexTensors
+
+    docs = make_docs(60, 5, 20, seed=12)
+    oidx, _ = build_oracle_index(docs, kmeans_niters=2)
+    lens = oidx.doc_lengths.clone()
+    lens[8] += lens[7]
+    lens[7] = 0  # document 7 becomes empty; its tokens now belong to document 8
+    o2 = po.OracleIndex(oidx.nbits, oidx.centroids, oidx.bucket_weights, oidx.ivf, oidx.ivf_lengths, oidx.doc_codes,
+                        oidx.doc_residuals, lens)
+    t = to_index_tensors(o2)
+    didx = DeviceIndex(t, cuda_device)
+    q = make_queries(2, 8, seed=13, docs=docs)
+    params = DeviceIndex.make_params(60, 4096, 8)
+    ids, scores, counts = didx.search(q.half().to(cuda_device), params)
+    torch.cuda.synchronize()
+    for b in range(2):
+        got = dict(zip(ids[b, : int(counts[b])].tolist(), scores[b, : int(counts[b])].tolist()))
+        if 7 in got:  # it is a candidate only through the IVF entries of its former tokens
+            assert got[7] == 8 * -10000.0
+            assert ids[b, int(counts[b]) - 1] == 7
+    emb = didx.reconstruct([7, 8])
+    assert emb[0].shape[0] == 0 and emb[1].shape[0] == int(lens[8])
