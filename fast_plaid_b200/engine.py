@@ -107,6 +107,7 @@ EXPORTED_SYMBOLS = [
     "fpb_shard_exact_records",
     "fpb_reconstruct",
     "fpb_token_scores",
+    "fpb_encode",
 ]
 
 
@@ -174,6 +175,8 @@ def load_library() -> ctypes.CDLL:
         lib.fpb_merge_shards.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
         lib.fpb_reconstruct.restype = i32
         lib.fpb_reconstruct.argtypes = [vp, vp, i32, vp, vp, vp]
+        lib.fpb_encode.restype = i32
+        lib.fpb_encode.argtypes = [i32, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp]
         lib.fpb_token_scores.restype = i32
         lib.fpb_token_scores.argtypes = [vp, vp, i32, vp, vp, i32, i64, vp, vp]
         _lib = lib
@@ -226,6 +229,26 @@ class IndexTensors:
     @property
     def dim(self) -> int:
         return int(self.centroids.shape[1])
+
+
+def encode_tokens(tokens: torch.Tensor, centroids: torch.Tensor, cutoffs: torch.Tensor,
+                  nbits: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Index-build encode step on the GPU (fpb_encode; create.rs:404-428): fp16 CUDA tokens [n, 128],
+    fp16 centroids [K, 128], f32 cutoffs -> (codes int32 [n], packed residuals u8 [n, 128*nbits/8])."""
+    _require_cuda()
+    lib = load_library()
+    dev = tokens.device
+    tokens = tokens.to(torch.float16).contiguous()
+    centroids = centroids.to(dev, torch.float16).contiguous()
+    cutoffs = cutoffs.to(dev, torch.float32).contiguous()
+    n, dim = tokens.shape
+    codes = torch.empty((n,), dtype=torch.int32, device=dev)
+    res = torch.empty((n, dim * nbits // 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.fpb_encode(dev.index, int(nbits), int(dim), int(centroids.shape[0]), centroids.data_ptr(),
+                              tokens.data_ptr(), n, cutoffs.data_ptr(), codes.data_ptr(), res.data_ptr(),
+                              torch.cuda.current_stream(dev).cuda_stream))
+    return codes, res
 
 
 def shard_tensors(data: IndexTensors, rank: int, world: int) -> tuple[IndexTensors, int]:

@@ -171,7 +171,14 @@ def train_codec(docs: list[torch.Tensor], centroids: torch.Tensor, nbits: int, s
 @torch.inference_mode()
 def encode(batch: torch.Tensor, centroids: torch.Tensor, centroids_t: torch.Tensor, cutoffs: torch.Tensor,
            nbits: int) -> tuple[torch.Tensor, torch.Tensor]:
-    """One batch of fp16 token rows -> (codes int64, packed residual bytes) (create.rs:404-428)."""
+    """One batch of fp16 token rows -> (codes int64, packed residual bytes) (create.rs:404-428).
+    On a CUDA device with dim = 128 this is the sm_100a encode kernel pair (tcgen05 argmax GEMM +
+    bucketize/pack, csrc/encode.cu); otherwise dense torch ops."""
+    if batch.is_cuda and batch.shape[1] == 128 and nbits in (2, 4):
+        from ..engine import encode_tokens
+
+        codes32, packed = encode_tokens(batch, centroids, cutoffs, nbits)
+        return codes32.to(torch.int64), packed
     codes = assign_codes(batch, centroids_t)
     res = batch - centroids.index_select(0, codes)
     buckets = torch.bucketize(res, cutoffs, out_int32=True, right=False)

@@ -222,6 +222,16 @@ int fpb_reconstruct(const fpb_index* index, const int32_t* d_doc_ids, int n, con
 int fpb_token_scores(const fpb_index* index, const void* d_queries, int Q, const int32_t* d_query_of,
                      const int32_t* d_doc_ids, int n, int64_t max_len, void* d_out, void* stream);
 
+/* ---- index build: the encode step of create_index (rust/index/create.rs:404-428) ----
+ * codes[t] = argmax_k fp16(<x_t, c_k>) (compress_into_codes, create.rs:148-170; ties -> smallest k),
+ * residuals[t] = packed bucket indices of fp16(x_t - c[codes[t]]) against `cutoffs`
+ * (bucketize right=false + LSB-first bits + big-endian packbits, create.rs:413-427, :176-184).
+ *   d_tokens f16 [n_tokens, dim], d_centroids f16 [n_centroids, dim], d_cutoffs f32 [(1<<nbits)-1]
+ *   d_codes i32 [n_tokens], d_residuals u8 [n_tokens, dim*nbits/8] */
+int fpb_encode(int device, int nbits, int dim, int64_t n_centroids, const void* d_centroids,
+               const void* d_tokens, int64_t n_tokens, const float* d_cutoffs, int32_t* d_codes,
+               uint8_t* d_residuals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
