@@ -10,7 +10,8 @@ Same algorithm and on-disk result as the reference's ``compute_kmeans`` + ``crea
 
 This module is not on the search hot path; it runs on whichever torch device it is given
 (CUDA on the B200 box, CPU in the container's tests) with dense torch ops.  The encode step
-(argmax GEMM + bucketize + pack) is the part scheduled to become an sm_100a kernel.
+(argmax GEMM + bucketize + pack) runs in the sm_100a kernels behind `fpb_encode`
+(csrc/encode.cu) when the tokens are on CUDA with dim=128; elsewhere it is dense torch ops.
 """
 
 from __future__ import annotations
