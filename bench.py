@@ -384,7 +384,8 @@ def run_b200(args) -> dict:
                         "Python list[list[(doc_id, score)]]"},
         "gpu_launches": (10 if world == 1 else 13) * args.steps,
         "clocks": clocks,
-        "roofline": {"kernel": "k5_maxsim_kernel (fused residual decompression + MaxSim)", "bound": "hbm",
+        "roofline": {"kernel": ("k5_maxsim_v4_kernel" if Q <= 32 else "k5_maxsim_v2_kernel") +
+                               " (fused residual decompression + MaxSim)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": stage_ms[i_ms]},
