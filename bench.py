@@ -33,6 +33,9 @@ CONFIGS = {
     # name: n_docs, doc_len, B, Q, top_k
     "cfg3": dict(n_docs=1_000_000, doc_len=300, B=64, Q=32, top_k=100,
                  desc="1M docs x 300 tok x 128-dim (nbits=4, K=262144), batch=64 queries x 32 tok, top_k=100"),
+    "cfg3c": dict(n_docs=1_000_000, doc_len=300, B=64, Q=32, top_k=100, topics=4096, mix=0.05,
+                  desc="clustered variant of cfg3: 4096 topics x 64 centroids, 5 % of the codes uniform "
+                       "(1M docs x 300 tok, K=262144), batch=64 queries x 32 tok, top_k=100"),
     "cfg2": dict(n_docs=100_000, doc_len=300, B=64, Q=32, top_k=100,
                  desc="100k docs x 300 tok x 128-dim (nbits=4, K=65536), batch=64 queries x 32 tok, top_k=100"),
     "cfg4": dict(n_docs=1_000_000, doc_len=300, B=256, Q=32, top_k=1000,
@@ -190,7 +193,8 @@ def run_b200(args) -> dict:
     n_docs = cfg["n_docs"]
     lo, hi = (n_docs * rank) // world, (n_docs * (rank + 1)) // world
     t0 = time.time()
-    data, base = synthetic_index(n_docs, cfg["doc_len"], DIM, NBITS, device, SEED_INDEX, doc_range=(lo, hi))
+    data, base = synthetic_index(n_docs, cfg["doc_len"], DIM, NBITS, device, SEED_INDEX, doc_range=(lo, hi),
+                                 topics=cfg.get("topics", 0), mix=cfg.get("mix", 0.05))
     didx = DeviceIndex(data, device, doc_id_base=base)
     del data
     torch.cuda.synchronize()
@@ -545,7 +549,8 @@ def run_reference(args) -> dict:
         from fast_plaid_b200.engine import DeviceIndex
         from fast_plaid_b200.index.synthetic import synthetic_index
 
-        data, _ = synthetic_index(cfg["n_docs"], cfg["doc_len"], DIM, NBITS, "cuda:0", SEED_INDEX)
+        data, _ = synthetic_index(cfg["n_docs"], cfg["doc_len"], DIM, NBITS, "cuda:0", SEED_INDEX,
+                                  topics=cfg.get("topics", 0), mix=cfg.get("mix", 0.05))
         didx = DeviceIndex(data, "cuda:0")
         del data
         q_host = make_query_batches(didx, cfg, N_QUERY_BATCHES, "cuda:0")

@@ -17,6 +17,13 @@ ranks is the same index:
 
 The decompressed tokens are centroid + per-dimension quantised Gaussian noise, renormalised,
 i.e. a valid PLAID index of a clustered corpus.
+
+`topics > 0` switches to the *clustered* variant SURVEY.md 8(d) asks to report next to the
+worst case: the K centroids are grouped into `topics` blocks of similar directions (block
+direction + 0.5 * noise, renormalised), every document belongs to one topic and draws a
+fraction `1 - mix` of its codes from its topic's block and `mix` uniformly.  A query token's
+nearest centroids then sit in one block and the candidate set shrinks from ~25 % of the index
+to a few per cent, which moves the time from the approximate stage to the fixed-cost stages.
 """
 
 from __future__ import annotations
@@ -37,7 +44,8 @@ def _normal_quantiles(n: int, sigma: float) -> torch.Tensor:
 @torch.inference_mode()
 def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, device: str = "cuda:0",
                     seed: int = 1234, doc_range: tuple[int, int] | None = None, ragged: bool = False,
-                    sigma: float = 0.05, docs_per_chunk: int = 25_000) -> tuple[IndexTensors, int]:
+                    sigma: float = 0.05, docs_per_chunk: int = 25_000, topics: int = 0,
+                    mix: float = 0.05) -> tuple[IndexTensors, int]:
     """Returns (tensors on `device`, doc_id_base).  `doc_range=(lo, hi)` generates only that
     slice of the global index (document sharding); ids in the IVF are then local."""
     dev = torch.device(device)
@@ -52,7 +60,17 @@ def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, d
         lengths = torch.full((n_docs,), doc_len, dtype=torch.int64)
     total_tokens = int(lengths.sum())
     K = build.num_partitions_for(float(total_tokens))
-    centroids = torch.nn.functional.normalize(torch.randn(K, dim, generator=g, device=dev), dim=-1).half()
+    centroids = torch.randn(K, dim, generator=g, device=dev)
+    block = 0
+    if topics > 0:
+        topics = min(topics, K)
+        block = K // topics  # K is a power of two; topics is clipped to a divisor below
+        while K % topics:
+            topics -= 1
+            block = K // topics
+        directions = torch.nn.functional.normalize(torch.randn(topics, dim, generator=g, device=dev), dim=-1)
+        centroids = directions.repeat_interleave(block, dim=0) + 0.5 * centroids / math.sqrt(dim)
+    centroids = torch.nn.functional.normalize(centroids, dim=-1).half()
     weights = _normal_quantiles(2**nbits, sigma).to(dev).half()
     pd = dim * nbits // 8
     my_lengths = lengths[lo:hi]
@@ -68,6 +86,14 @@ def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, d
         gc.manual_seed(seed * 1_000_003 + c0)
         n = int(offs[c1] - offs[c0])
         cc = torch.randint(0, K, (n,), generator=gc, device=dev, dtype=torch.int32)
+        if topics > 0:
+            # topic of a document: a fixed hash of its global id; tokens keep the uniform draw with
+            # probability `mix`, otherwise they land in the topic's block
+            doc_of_tok = torch.repeat_interleave(torch.arange(c0, c1, device=dev), lengths[c0:c1].to(dev))
+            topic = (doc_of_tok * 2654435761) % topics
+            in_block = topic * block + (cc.long() % block)
+            keep = torch.rand(n, generator=gc, device=dev) < mix
+            cc = torch.where(keep, cc.long(), in_block).to(torch.int32)
         rr = torch.randint(0, 256, (n, pd), generator=gc, device=dev, dtype=torch.uint8)
         # clip the chunk to [lo, hi)
         a = max(c0, lo)
