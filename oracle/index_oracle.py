@@ -61,15 +61,16 @@ def num_partitions_for(n_embeddings: float) -> int:
 def kmeans(data: torch.Tensor, k: int, niters: int, seed: int, max_points_per_centroid: int = 256) -> torch.Tensor:
     """Lloyd iterations as in kmeans.py:60-223 (CPU => fp32 compute, kmeans.py:113-114)."""
     torch.manual_seed(seed)  # kmeans.py:236
-    data = data.float()
+    dn = (data**2).sum(1)  # kmeans.py:241: squared norms in the data's own dtype (fp16 from compute_kmeans)
     n = data.shape[0]
     if max_points_per_centroid is not None and n > k * max_points_per_centroid:  # :119-126
-        data = data[torch.randperm(n)[: k * max_points_per_centroid]]
+        sel = torch.randperm(n)[: k * max_points_per_centroid]
+        data, dn = data[sel], dn[sel]
         n = data.shape[0]
     if n < k:
         raise ValueError(f"Number of training points ({n}) is less than k ({k}).")
+    data, dn = data.float(), dn.float()  # CPU => fp32 compute (:113-114, :148-153)
     centroids = data[torch.randperm(n)[:k]].clone()  # :133-134
-    dn = (data**2).sum(1)
     for _ in range(niters):
         cn = (centroids**2).sum(1)
         best = torch.empty(n, dtype=torch.int64)

@@ -16,7 +16,7 @@ from oracle import plaid_oracle as po
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "small_*.pt")))
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])

@@ -14,7 +14,7 @@ from util import build_oracle_index, make_docs, make_queries, oracle_exact_score
 
 from oracle import plaid_oracle as po
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "small_*.pt")))
 
 
 def _load_golden(path):
@@ -181,3 +181,38 @@ def test_zero_length_document_scores_like_the_reference():
     q = make_queries(1, 8, seed=1)[0]
     s = oracle_exact_scores(o2, q, [3, 4])
     assert float(s[0]) == 8 * -10000.0
+
+
+def test_kmeans_restatement_reproduces_reference_outputs():
+    """tests/golden/kmeans_ref.pt holds inputs and OUTPUTS of the reference's own Lloyd loop
+    (python/fast_plaid/search/kmeans.py:60-223, imported unmodified by
+    tests/golden/make_kmeans_golden.py).  The oracle's restatement must reproduce the centroids
+    bit for bit: plain run, the n > k*max_points_per_centroid subsampling path and the
+    empty-cluster reseed path."""
+    from oracle import index_oracle as io
+
+    blob = torch.load(os.path.join(os.path.dirname(__file__), "golden", "kmeans_ref.pt"), weights_only=False)
+    assert "reference" in blob["source"]
+    assert len(blob["cases"]) == 3
+    for c in blob["cases"]:
+        got = io.kmeans(c["data"], c["k"], c["niters"], c["seed"], c["max_points_per_centroid"])
+        assert got.shape == c["centroids"].shape
+        assert torch.equal(got, c["centroids"]), float((got - c["centroids"]).abs().max())
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/python/fast_plaid/search/kmeans.py"),
+                    reason="reference tree not mounted (GPU box)")
+def test_kmeans_restatement_against_the_live_reference_code():
+    """Same check against the reference file itself (fresh random problem, not the fixture)."""
+    import importlib.util
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_kmeans_golden as mk
+    from oracle import index_oracle as io
+
+    mod = mk.load_reference_kmeans()
+    g = torch.Generator().manual_seed(99)
+    x = torch.nn.functional.normalize(torch.randn(1500, 24, generator=g), dim=-1).half()
+    ref_c, _ = mk.run_case(mod, x, 32, 3, 5, 256)
+    assert torch.equal(io.kmeans(x, 32, 3, 5, 256), ref_c)
