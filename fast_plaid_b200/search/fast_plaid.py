@@ -90,19 +90,7 @@ class FastPlaid:
         merge with the other ranks through ``torch.distributed`` (NCCL); ``"auto"`` takes
         rank/world from an initialised process group.
         """
-        if device is not None and isinstance(device, str):
-            self.devices = [device]
-        elif isinstance(device, list):
-            self.devices = device
-        elif torch.cuda.is_available():
-            self.devices = [f"cuda:{i}" for i in range(torch.cuda.device_count())]
-        else:
-            self.devices = ["cpu"]
-        self.devices = ["cuda:0" if d == "cuda" else d for d in self.devices]
-        self.devices = list(dict.fromkeys(self.devices))
-        for d in self.devices:
-            if d != "cpu" and not (d.startswith("cuda:") and d[5:].isdigit()):
-                raise ValueError(f"Unsupported device string: '{d}'")  # load.rs:16-37
+        self.devices = self._resolve_devices(device)
 
         self.index = index
         self.low_memory = low_memory
@@ -235,6 +223,27 @@ class FastPlaid:
                 idx.close()
 
     # ------------------------------------------------------------------ create / update / delete
+    @staticmethod
+    def _resolve_devices(device: str | list[str] | None) -> list[str]:
+        """Device list semantics of fast_plaid.py:350-362: one string, a list, or by default every
+        visible GPU (else "cpu"); bare "cuda" means cuda:0; duplicates dropped, order kept.
+        Anything that is not "cpu" / "cuda:N" is refused like parse_device (load.rs:16-37)."""
+        if isinstance(device, str):
+            wanted = [device]
+        elif isinstance(device, list):
+            wanted = list(device)
+        else:
+            n_gpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
+            wanted = [f"cuda:{i}" for i in range(n_gpu)] or ["cpu"]
+        resolved: list[str] = []
+        for d in wanted:
+            d = "cuda:0" if d == "cuda" else d
+            if d != "cpu" and not (d.startswith("cuda:") and d[5:].isdigit()):
+                raise ValueError(f"Unsupported device string: '{d}'")
+            if d not in resolved:
+                resolved.append(d)
+        return resolved
+
     def _format_embeddings(self, embeddings):
         if isinstance(embeddings, torch.Tensor):
             return embeddings.squeeze(0) if embeddings.dim() == 3 and embeddings.shape[0] == 1 else embeddings
@@ -357,15 +366,43 @@ class FastPlaid:
         return self
 
     # ------------------------------------------------------------------ search
+    def _loaded_indices(self) -> dict[str, Any]:
+        """Snapshot of the per-device handles, reloading first if another process changed the
+        directory (non-blocking try, then blocking if some device has no handle yet)."""
+        for blocking in (False, True):
+            self._check_and_reload_index(blocking=blocking)
+            with self._index_swap_lock:
+                snapshot = dict(self.indices)
+            if all(h is not None for h in snapshot.values()):
+                break
+        return snapshot
+
+    @staticmethod
+    def _as_query_tensor(queries_embeddings) -> torch.Tensor:
+        """A list of [Q_i, D] (or [1, Q_i, D]) tensors becomes one zero-padded [B, Qmax, D] tensor
+        (fast_plaid.py:772-780); zero rows score 0 against everything and never probe."""
+        if not isinstance(queries_embeddings, list):
+            return queries_embeddings
+        rows = [q.squeeze(0) if q.dim() == 3 else q for q in queries_embeddings]
+        return torch.nn.utils.rnn.pad_sequence(rows, batch_first=True, padding_value=0.0)
+
+    @staticmethod
+    def _per_query_subsets(subset, num_queries: int):
+        """`subset` may be None / [] (no filter), one id, one id list shared by all queries, or
+        one list per query (fast_plaid.py:784-793)."""
+        if subset is None or (isinstance(subset, list) and not subset):
+            return None
+        if isinstance(subset, int):
+            subset = [subset]
+        if isinstance(subset[0], int):
+            return [subset] * num_queries
+        if len(subset) != num_queries:
+            raise ValueError("Subset length must match number of queries.")
+        return subset
+
     def _prepare_search(self, queries_embeddings, subset):
         """fast_plaid.py:743-795"""
-        self._check_and_reload_index(blocking=False)
-        with self._index_swap_lock:
-            search_indices = dict(self.indices)
-        if any(idx is None for idx in search_indices.values()):
-            self._check_and_reload_index(blocking=True)
-            with self._index_swap_lock:
-                search_indices = dict(self.indices)
+        search_indices = self._loaded_indices()
         if not os.path.exists(os.path.join(self.index, "metadata.json")):
             raise FileNotFoundError(
                 f"Index metadata not found in '{self.index}'. Please create the index before searching."
@@ -380,22 +417,8 @@ class FastPlaid:
                 raise RuntimeError(
                     f"Index could not be loaded on device '{device}'. Check CUDA memory or device availability."
                 )
-        if isinstance(queries_embeddings, list):
-            queries_embeddings = torch.nn.utils.rnn.pad_sequence(
-                sequences=[e[0] if e.dim() == 3 else e for e in queries_embeddings],
-                batch_first=True,
-                padding_value=0.0,
-            )
-        num_queries = queries_embeddings.shape[0]
-        if subset is not None:
-            if isinstance(subset, int):
-                subset = [subset] * num_queries
-            if isinstance(subset, list) and len(subset) == 0:
-                subset = None
-            if isinstance(subset, list) and isinstance(subset[0], int):
-                subset = [subset] * num_queries
-            if subset is not None and len(subset) != num_queries:
-                raise ValueError("Subset length must match number of queries.")
+        queries_embeddings = self._as_query_tensor(queries_embeddings)
+        subset = self._per_query_subsets(subset, queries_embeddings.shape[0])
         return search_indices, queries_embeddings, subset
 
     def _search_device(self, idx: DeviceIndex, queries: torch.Tensor, params,
