@@ -123,6 +123,132 @@ k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* 
   }
 }
 
+// Shuffle-free variant.  The ncu capture of the kernel above (profiles/r01b_top3_raw.csv) shows the
+// L1TEX data pipe 96.5 % busy: 32.1 M of its 38.6 M wavefronts per SM are the row gathers (one per
+// row, the floor of this formulation) and 6.5 M are the __shfl_sync that hand each code to the LPR
+// lanes fetching its row -- shuffles run through the same pipe.  Here the LPR lanes of a group
+// load "their" LPR consecutive codes themselves with one vector load (the lanes of a group read
+// the same 4*LPR bytes: a broadcast, one wavefront for the warp): the document is walked in
+// 32-token windows aligned to absolute multiples of 32 tokens, so the vector loads are aligned
+// whatever the document offset; tokens outside [o0, o0+len) are masked.  max() is order-free,
+// so the values are bit-identical to the shuffle kernel.
+template <int LPR>
+__device__ __forceinline__ void load_codes(int (&c)[LPR], const int32_t* p) {
+  if constexpr (LPR == 2) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(p));
+    c[0] = v.x; c[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < LPR / 4; ++i) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(p) + i);
+      c[4 * i + 0] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+    }
+  }
+}
+
+template <int LPR, int UNROLL, int MINB>
+__global__ void __launch_bounds__(K3_THREADS, MINB)
+k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
+                     const int32_t* __restrict__ codes, int64_t n_codes, const int32_t* __restrict__ cand,
+                     int cand_cap, const int32_t* __restrict__ n_cand, int32_t* __restrict__ work, int B,
+                     float* __restrict__ approx) {
+  constexpr int QP = LPR * 8;
+  __shared__ int s_b, s_c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const __half2 sentinel = __float2half2_rn(FPB_PAD_SENTINEL);
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const int c = atomicAdd(&work[B + 1], 1);
+      if (c >= work[B]) {
+        s_b = -1;
+      } else {
+        int lo = 0, hi = B - 1;  // largest b with work[b] <= c
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (work[mid] <= c) lo = mid; else hi = mid - 1;
+        }
+        s_b = lo;
+        s_c = c - work[lo];
+      }
+    }
+    __syncthreads();
+    const int b = s_b;
+    if (b < 0) return;
+    const int n = n_cand[b];
+    const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP) + sub;
+    const int32_t* cb = cand + int64_t(b) * cand_cap;
+    float* ab = approx + int64_t(b) * cand_cap;
+
+    for (int i = 0; i < K3_DOCS_PER_CHUNK / 8; ++i) {
+      const int idx = s_c * K3_DOCS_PER_CHUNK + i * 8 + warp;
+      if (idx >= n) break;
+      const int d = cb[idx];
+      const int64_t o0 = doc_offsets[d];
+      const int len = int(doc_offsets[d + 1] - o0);
+      // frame: token f of the frame is absolute token w0 + f; the document is [lo, hi)
+      const int64_t w0 = o0 & ~int64_t(31);
+      const int lo = int(o0 - w0), hi = lo + len;
+      const int32_t* cw = codes + w0 + grp * LPR;
+      // the last window may reach past the end of the code array: lanes whose LPR codes are not all
+      // inside it take the scalar path (at most once per index)
+      const int64_t readable = n_codes - (w0 + grp * LPR);
+      __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
+      for (int f0 = 0; f0 < hi; f0 += 32 * UNROLL) {
+        int c[UNROLL][LPR];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int fo = f0 + u * 32;
+          if (fo + LPR <= readable) {
+            load_codes<LPR>(c[u], cw + fo);
+          } else {
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) c[u][j] = (fo + j < readable) ? __ldg(cw + fo + j) : 0;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+          for (int j = 0; j < LPR; ++j) {
+            const int f = f0 + u * 32 + grp * LPR + j;
+            if (unsigned(f - lo) < unsigned(len)) {
+              const uint4 v = __ldg(Sb + int64_t(c[u][j]) * LPR);
+              m0 = __hmax2(m0, u32_as_half2(v.x));
+              m1 = __hmax2(m1, u32_as_half2(v.y));
+              m2 = __hmax2(m2, u32_as_half2(v.z));
+              m3 = __hmax2(m3, u32_as_half2(v.w));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) {
+        m0 = __hmax2(m0, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m0), off)));
+        m1 = __hmax2(m1, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m1), off)));
+        m2 = __hmax2(m2, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m2), off)));
+        m3 = __hmax2(m3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m3), off)));
+      }
+      const int col0 = sub * 8;
+      float s = 0.f;
+      const float2 f0 = __half22float2(m0), f1 = __half22float2(m1), f2 = __half22float2(m2),
+                   f3 = __half22float2(m3);
+      if (col0 + 0 < Q) s += f0.x;
+      if (col0 + 1 < Q) s += f0.y;
+      if (col0 + 2 < Q) s += f1.x;
+      if (col0 + 3 < Q) s += f1.y;
+      if (col0 + 4 < Q) s += f2.x;
+      if (col0 + 5 < Q) s += f2.y;
+      if (col0 + 6 < Q) s += f3.x;
+      if (col0 + 7 < Q) s += f3.y;
+#pragma unroll
+      for (int off = 1; off < LPR; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) ab[idx] = s;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // K3b: top-n_dec by (approx desc, candidate index asc) -- candidate index order is doc id
 // order, so this is the canonical rule "larger score, then smaller doc id".  Equivalent to
@@ -287,14 +413,39 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
                                                              ix->doc_codes, ws.cand(), L.cand_cap, ws.n_cand(), \
                                                              ws.work(), L.B, ws.approx())
   // measured on cfg-3 (ms): U1/M6 26.2, U2/M6 20.4, U1/M8 23.5, U2/M8 20.8, U4/M4 22.4
-  switch (variant) {
+#define K3_LAUNCH_NSH(U, M)                                                                                  \
+  k3_approx_nsh_kernel<LPR, U, M><<<blocks, K3_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets,         \
+                                                                 ix->doc_codes, ix->E, ws.cand(), L.cand_cap,  \
+                                                                 ws.n_cand(), ws.work(), L.B, ws.approx())
+  if constexpr (LPR <= 8) {
+    // the vector code loads need a 16-byte aligned code array (any torch allocation is)
+    const bool aligned = (reinterpret_cast<uintptr_t>(ix->doc_codes) & 15u) == 0;
+    if (aligned && (variant == 0 || variant >= 10)) {
+      switch (variant) {
+        case 0: K3_LAUNCH_NSH(2, 6); break;  // default: 20.0-20.2 ms on cfg-3 (shuffle kernel: 20.9-21.0 in the same session)
+        case 10: K3_LAUNCH_NSH(1, 6); break;
+        case 11: K3_LAUNCH_NSH(2, 6); break;
+        case 12: K3_LAUNCH_NSH(2, 5); break;
+        case 13: K3_LAUNCH_NSH(1, 8); break;
+        case 14: K3_LAUNCH_NSH(2, 7); break;
+        case 15: K3_LAUNCH_NSH(2, 8); break;
+        case 16: K3_LAUNCH_NSH(3, 6); break;
+        case 17: K3_LAUNCH_NSH(4, 6); break;
+        default: K3_LAUNCH_NSH(3, 5); break;
+      }
+      FPB_LAUNCH_CHECK("k3_approx_nsh");
+      return FPB_OK;
+    }
+  }
+  switch (variant) {  // shuffle kernel: Qp > 64, unaligned code arrays, or FPB_K3_VARIANT=1..5
     case 1: K3_LAUNCH(1, 6); break;
     case 2: K3_LAUNCH(2, 7); break;
     case 3: K3_LAUNCH(3, 5); break;
     case 4: K3_LAUNCH(3, 6); break;
-    default: K3_LAUNCH(2, 6); break;
+    default: K3_LAUNCH(2, 6); break;  // also FPB_K3_VARIANT=5
   }
 #undef K3_LAUNCH
+#undef K3_LAUNCH_NSH
   FPB_LAUNCH_CHECK("k3_approx");
   return FPB_OK;
 }
