@@ -388,7 +388,7 @@ def run_b200(args) -> dict:
                         "Python list[list[(doc_id, score)]]"},
         "gpu_launches": (10 if world == 1 else 13) * args.steps,
         "clocks": clocks,
-        "roofline": {"kernel": ("k5_maxsim_v4_kernel" if Q <= 32 else "k5_maxsim_v2_kernel") +
+        "roofline": {"kernel": ("k5_maxsim_v4_kernel" if Q <= 32 else "k5_maxsim_v5_kernel") +
                                " (fused residual decompression + MaxSim)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src,

@@ -420,7 +420,9 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   if constexpr (LPR <= 8) {
     // the vector code loads need a 16-byte aligned code array (any torch allocation is)
     const bool aligned = (reinterpret_cast<uintptr_t>(ix->doc_codes) & 15u) == 0;
-    if (aligned && (variant == 0 || variant >= 10)) {
+    // default: shuffle-free up to Qp = 32; at Qp = 64 (8 codes per lane) the shuffle kernel is faster
+    // (cfg-5: 10.55 vs 11.31 ms)
+    if (aligned && ((variant == 0 && LPR <= 4) || variant >= 10)) {
       switch (variant) {
         case 0: K3_LAUNCH_NSH(2, 6); break;  // default: 20.0-20.2 ms on cfg-3 (shuffle kernel: 20.9-21.0 in the same session)
         case 10: K3_LAUNCH_NSH(1, 6); break;

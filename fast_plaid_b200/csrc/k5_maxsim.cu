@@ -359,27 +359,26 @@ int launch_k5_q(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
 }  // namespace
 
 int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
-  // FPB_K5 = v1 | v2 | v3 | v4 pins one implementation (A/B measurements).  v1 and v2 are
-  // bit-identical; v3/v4 feed the tensor core in a different k order (fp32 accumulation order
-  // is implementation-defined in the reference too).
-  // Default: v4, then v2, then v1 (cfg-3: v1 2.71 ms, v2 1.67 ms, v3/tcgen05 2.06 ms).
+  // FPB_K5 = v1 | v2 | v4 | v5 pins one implementation (A/B measurements).  v1 and v2 are bit-identical;
+  // v4/v5 feed the tensor core in a different k order (fp32 accumulation order is
+  // implementation-defined in the reference too).
+  // Default (dim 128, nbits 4): Qp <= 32 -> v4 (cfg-3: v1 2.71, v2 1.67, v5 1.51, v4 1.24 ms);
+  // 32 < Qp <= 128 -> v5 (cfg-5: v2 3.27, v5 2.50 ms); everything else -> v1.
   static const char* pin = getenv("FPB_K5");
-  const bool allow_v3 = pin && pin[1] == '3';
-  const bool allow_v4 = !pin || pin[1] == '4';
-  const bool allow_v2 = !pin || pin[1] == '2' || pin[1] == '4';
-  if (allow_v3) {
-    bool handled = false;
-    const int rc = launch_maxsim_v3(ix, ws, st, &handled);
+  const char want = pin ? pin[1] : 0;
+  const int qp = ws.L->Qp;
+  bool handled = false;
+  int rc = FPB_OK;
+  if (want == '5' || (!want && qp > 32)) {
+    rc = launch_maxsim_v5(ix, ws, st, &handled);
     if (rc != FPB_OK || handled) return rc;
   }
-  if (allow_v4) {
-    bool handled = false;
-    const int rc = launch_maxsim_v4(ix, ws, st, &handled);
+  if (want == '4' || !want) {
+    rc = launch_maxsim_v4(ix, ws, st, &handled);
     if (rc != FPB_OK || handled) return rc;
   }
-  if (allow_v2) {
-    bool handled = false;
-    const int rc = launch_maxsim_v2(ix, ws, st, &handled);
+  if (want != '1') {
+    rc = launch_maxsim_v2(ix, ws, st, &handled);
     if (rc != FPB_OK || handled) return rc;
   }
 #define CALL(DD, NB) return launch_k5_q<DD, NB>(ix, ws, st);

@@ -37,8 +37,8 @@ int launch_approx(const fpb_index* ix, const Ws& ws, cudaStream_t st);          
 int launch_select(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3b
 int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K5 (dispatch)
 int launch_maxsim_v2(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v2 (128/4)
-int launch_maxsim_v3(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v3 (tcgen05)
 int launch_maxsim_v4(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v4 (register operands)
+int launch_maxsim_v5(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v5 (tcgen05, 20 decode warps)
 int launch_rank(const fpb_index* ix, const Ws& ws, int top_k, int64_t* d_out_ids, float* d_out_scores,
                 int32_t* d_out_counts, cudaStream_t st);                          // K6
 int launch_emit_keys(const fpb_index* ix, const Ws& ws, uint64_t* d_keys, cudaStream_t st);

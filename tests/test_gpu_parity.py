@@ -30,6 +30,7 @@ CONFIGS = {
     "dim64": (500, 20, 80, 64, 4, 4, 20, 10, 256, 8, True),
     "probe1": (500, 20, 80, 128, 4, 4, 16, 5, 64, 1, True),
     "q64": (300, 50, 120, 128, 4, 3, 64, 10, 256, 16, True),
+    "q100": (300, 10, 90, 128, 4, 2, 100, 10, 256, 8, True),
 }
 
 _cache: dict = {}
