@@ -47,7 +47,7 @@ void fpb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* fpb_last_error(void) { return g_err; }
-extern "C" int fpb_abi_version(void) { return 2; }
+extern "C" int fpb_abi_version(void) { return 3; }  // 3: fpb_shard_subset_begin / fpb_shard_subset_keys
 
 static int bitrev(int x, int nbits) {
   int r = 0;

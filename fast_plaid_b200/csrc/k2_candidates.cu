@@ -118,8 +118,9 @@ int launch_compact(const uint32_t* bitmap, const uint32_t* mask, int words, int3
   return FPB_OK;
 }
 
-int launch_subset(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const int64_t* d_offsets,
-                  int64_t max_len, cudaStream_t st) {
+// marks the per-query document bitmap and the bitmap of centroids those documents touch (no compaction)
+int launch_subset_mark(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const int64_t* d_offsets,
+                       int64_t max_len, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   if (L.off_sbitmap == L.off_cbitmap) {
     fpb_set_error("subset search needs a workspace laid out with FPB_FLAG_SUBSET");
@@ -134,7 +135,34 @@ int launch_subset(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const
                                              L.cbitmap_words);
     FPB_LAUNCH_CHECK("subset_mark");
   }
+  return FPB_OK;
+}
+
+int launch_subset_compact(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
   return launch_compact(ws.cbitmap(), nullptr, L.cbitmap_words, ws.clist(), int(ix->K), ws.n_clist(), L.B, st);
+}
+
+namespace {
+// cbitmap[i] = OR over shards of all[s][i]   (document-sharded subset search: the centroids the
+// subset documents touch are the union over the shards that hold them)
+__global__ void or_bitmaps_kernel(const uint32_t* __restrict__ all, int n_shards, int64_t words,
+                                  uint32_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < words; i += int64_t(gridDim.x) * blockDim.x) {
+    uint32_t v = 0;
+    for (int s = 0; s < n_shards; ++s) v |= all[int64_t(s) * words + i];
+    out[i] = v;
+  }
+}
+}  // namespace
+
+int launch_subset_merge(const fpb_index* ix, const Ws& ws, const uint32_t* d_all, int n_shards, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
+  const int64_t words = int64_t(L.B) * L.cbitmap_words;
+  const int blocks = int((words + 255) / 256 < 1184 ? (words + 255) / 256 : 1184);
+  or_bitmaps_kernel<<<blocks, 256, 0, st>>>(d_all, n_shards, words, ws.cbitmap());
+  FPB_LAUNCH_CHECK("or_bitmaps");
+  return launch_subset_compact(ix, ws, st);
 }
 
 int launch_candidates(const fpb_index* ix, const Ws& ws, bool subset, cudaStream_t st) {
@@ -147,4 +175,10 @@ int launch_candidates(const fpb_index* ix, const Ws& ws, bool subset, cudaStream
   FPB_LAUNCH_CHECK("k2_mark");
   return launch_compact(ws.bitmap(), subset ? ws.sbitmap() : nullptr, L.bitmap_words, ws.cand(), L.cand_cap,
                         ws.n_cand(), L.B, st);
+}
+
+int launch_subset(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const int64_t* d_offsets,
+                  int64_t max_len, cudaStream_t st) {
+  const int rc = launch_subset_mark(ix, ws, d_ids, d_offsets, max_len, st);
+  return rc != FPB_OK ? rc : launch_subset_compact(ix, ws, st);
 }

@@ -29,6 +29,10 @@ int launch_centroid_scores(const fpb_index* ix, const Ws& ws, cudaStream_t st); 
 int launch_centroid_scores_v2(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K1 on tcgen05
 int launch_probe(const fpb_index* ix, const Ws& ws, bool subset, cudaStream_t st);       // K1b
 int launch_candidates(const fpb_index* ix, const Ws& ws, bool subset, cudaStream_t st);  // K2
+int launch_subset_mark(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const int64_t* d_offsets,
+                       int64_t max_len, cudaStream_t st);
+int launch_subset_compact(const fpb_index* ix, const Ws& ws, cudaStream_t st);
+int launch_subset_merge(const fpb_index* ix, const Ws& ws, const uint32_t* d_all, int n_shards, cudaStream_t st);
 int launch_subset(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const int64_t* d_offsets,
                   int64_t max_len, cudaStream_t st);                                      // subset structures
 int launch_compact(const uint32_t* bitmap, const uint32_t* mask, int words, int32_t* out, int cap, int32_t* n_out,

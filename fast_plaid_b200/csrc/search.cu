@@ -154,6 +154,45 @@ extern "C" int fpb_shard_approx_keys(const fpb_index* ix, const void* d_queries,
   return launch_emit_keys(ix, ws, d_keys, st);
 }
 
+extern "C" int fpb_shard_subset_begin(const fpb_index* ix, const void* d_queries, int B, int Q, const fpb_params* p,
+                                      const int32_t* d_subset_ids, const int64_t* d_subset_offsets,
+                                      int64_t max_subset_len, void* d_ws, size_t ws_bytes,
+                                      uint32_t* d_cbitmap_out, void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, true));
+  if (!d_queries || !d_subset_offsets || !d_cbitmap_out || !(p->flags & FPB_FLAG_SUBSET)) {
+    fpb_set_error("fpb_shard_subset_begin: NULL pointer or FPB_FLAG_SUBSET not set");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  FPB_TRY(launch_pad_queries(ix, ws, static_cast<const __half*>(d_queries), st));
+  FPB_TRY(launch_centroid_scores(ix, ws, st));
+  FPB_TRY(launch_subset_mark(ix, ws, d_subset_ids, d_subset_offsets, max_subset_len, st));
+  FPB_CUDA_CHECK(cudaMemcpyAsync(d_cbitmap_out, ws.cbitmap(), size_t(L.B) * L.cbitmap_words * 4,
+                                 cudaMemcpyDeviceToDevice, st));
+  return FPB_OK;
+}
+
+extern "C" int fpb_shard_subset_keys(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
+                                     size_t ws_bytes, const uint32_t* d_all_cbitmaps, int n_shards,
+                                     uint64_t* d_keys, void* stream) {
+  fpb_layout L;
+  FPB_TRY(prepare(ix, B, Q, p, d_ws, ws_bytes, &L, true));
+  if (!d_all_cbitmaps || !d_keys || n_shards < 1 || !(p->flags & FPB_FLAG_SUBSET)) {
+    fpb_set_error("fpb_shard_subset_keys: bad arguments or FPB_FLAG_SUBSET not set");
+    return FPB_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Ws ws{&L, static_cast<char*>(d_ws)};
+  FPB_TRY(launch_subset_merge(ix, ws, d_all_cbitmaps, n_shards, st));
+  FPB_TRY(launch_probe(ix, ws, true, st));
+  FPB_TRY(launch_candidates(ix, ws, true, st));
+  FPB_TRY(launch_approx(ix, ws, st));
+  FPB_TRY(launch_select(ix, ws, st));
+  return launch_emit_keys(ix, ws, d_keys, st);
+}
+
 extern "C" int fpb_shard_apply_threshold(const fpb_index* ix, const uint64_t* d_all_keys, int n_shards,
                                          int shard_rank, int B, int Q, const fpb_params* p, void* d_ws,
                                          size_t ws_bytes, void* stream) {

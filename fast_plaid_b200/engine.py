@@ -103,6 +103,8 @@ EXPORTED_SYMBOLS = [
     "fpb_search_shard",
     "fpb_merge_shards",
     "fpb_shard_approx_keys",
+    "fpb_shard_subset_begin",
+    "fpb_shard_subset_keys",
     "fpb_shard_apply_threshold",
     "fpb_shard_exact_records",
     "fpb_reconstruct",
@@ -167,6 +169,10 @@ def load_library() -> ctypes.CDLL:
         lib.fpb_search_shard.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
         lib.fpb_shard_approx_keys.restype = i32
         lib.fpb_shard_approx_keys.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
+        lib.fpb_shard_subset_begin.restype = i32
+        lib.fpb_shard_subset_begin.argtypes = [vp, vp, i32, i32, ctypes.POINTER(FpbParams), vp, vp, i64, vp, sz, vp, vp]
+        lib.fpb_shard_subset_keys.restype = i32
+        lib.fpb_shard_subset_keys.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, i32, vp, vp]
         lib.fpb_shard_apply_threshold.restype = i32
         lib.fpb_shard_apply_threshold.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
         lib.fpb_shard_exact_records.restype = i32
@@ -373,6 +379,11 @@ class DeviceIndex:
                     flags: int = 0) -> FpbParams:
         return FpbParams(int(n_ivf_probe), int(n_full_scores), int(top_k), int(batch_size), int(flags))
 
+    @staticmethod
+    def with_subset_flag(params: FpbParams) -> FpbParams:
+        return FpbParams(params.n_ivf_probe, params.n_full_scores, params.top_k, params.batch_size,
+                         params.flags | FPB_FLAG_SUBSET)
+
     def layout(self, B: int, Q: int, params: FpbParams) -> FpbLayout:
         lay = FpbLayout()
         _check(self._lib.fpb_workspace_layout(self._handle, B, Q, ctypes.byref(params), ctypes.byref(lay)))
@@ -549,6 +560,33 @@ class DeviceIndex:
         with torch.cuda.device(self.device):
             _check(self._lib.fpb_shard_approx_keys(self._handle, queries.data_ptr(), B, Q, ctypes.byref(params),
                                                    buf.data_ptr(), buf.numel(), keys.data_ptr(), self._stream()))
+        return keys
+
+    def shard_subset_begin(self, queries: torch.Tensor, params: FpbParams, subset: list[list[int]]) -> torch.Tensor:
+        """Sharded search with a `subset`, step 1a: centroid scores and this shard's bitmaps.  Returns the
+        shard's centroid bitmap, int32 [B, cbitmap_words], for the all-gather.  `params.flags` must carry
+        FPB_FLAG_SUBSET; `subset` holds GLOBAL document ids."""
+        queries = queries.contiguous()
+        B, Q, _ = queries.shape
+        buf, lay = self.workspace(B, Q, params)
+        sid, soff, smax = self._subset_csr(subset, 0, B)
+        cb = torch.empty((B, lay.cbitmap_words), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self._lib.fpb_shard_subset_begin(self._handle, queries.data_ptr(), B, Q, ctypes.byref(params),
+                                                    sid.data_ptr(), soff.data_ptr(), smax, buf.data_ptr(),
+                                                    buf.numel(), cb.data_ptr(), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # sid/soff are temporaries
+        return cb
+
+    def shard_subset_keys(self, all_cbitmaps: torch.Tensor, Q: int, params: FpbParams) -> torch.Tensor:
+        """Step 1b: all_cbitmaps int32 [n_shards, B, cbitmap_words] (all-gathered) -> int64 keys [B, R]."""
+        n_shards, B, _ = all_cbitmaps.shape
+        buf, lay = self.workspace(B, Q, params)
+        keys = torch.empty((B, lay.R), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self._lib.fpb_shard_subset_keys(self._handle, B, Q, ctypes.byref(params), buf.data_ptr(),
+                                                   buf.numel(), all_cbitmaps.contiguous().data_ptr(), n_shards,
+                                                   keys.data_ptr(), self._stream()))
         return keys
 
     def shard_exact_records(self, all_keys: torch.Tensor, rank: int, Q: int, params: FpbParams) -> torch.Tensor:

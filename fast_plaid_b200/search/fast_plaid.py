@@ -427,9 +427,7 @@ class FastPlaid:
         if queries.dim() != 3:
             raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries.shape)}")
         if self.shard is not None:
-            if subset is not None:
-                raise NotImplementedError("subset= with a document-sharded index is not supported yet")
-            return self._search_sharded(idx, queries, params)
+            return self._search_sharded(idx, queries, params, subset)
         if subset is not None:
             q16 = queries.to(torch.float16).to(idx.device)
             ids, scores, counts = idx.search(q16, params, subset=subset)
@@ -442,27 +440,34 @@ class FastPlaid:
         ids, scores, counts = idx.search_host(queries, params)
         return _results_to_lists(ids, scores, counts)
 
-    def _search_sharded(self, idx: DeviceIndex, queries: torch.Tensor, params) -> list[list[tuple[int, float]]]:
+    def _search_sharded(self, idx: DeviceIndex, queries: torch.Tensor, params,
+                        subset: list[list[int]] | None = None) -> list[list[tuple[int, float]]]:
         """Document-sharded search: local records -> NCCL all-gather -> global prune + rank."""
         import torch.distributed as dist
+
+        def all_gather(t: torch.Tensor) -> torch.Tensor:
+            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+            if world > 1:
+                dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
+            else:
+                out.copy_(t.unsqueeze(0))
+            return out
 
         q16 = queries.to(device=idx.device, dtype=torch.float16, non_blocking=True)
         rank, world = self.shard
         # step 1: local pruning, all-gather of the approximate-score keys
-        keys = idx.shard_approx_keys(q16, params)
-        all_keys = torch.empty((world,) + tuple(keys.shape), dtype=torch.int64, device=idx.device)
-        if world > 1:
-            dist.all_gather_into_tensor(all_keys.view(-1), keys.view(-1))
+        if subset is None:
+            keys = idx.shard_approx_keys(q16, params)
         else:
-            all_keys.copy_(keys.unsqueeze(0))
+            # the probe is restricted to the centroids the subset documents touch (search.rs:494-517);
+            # with sharded documents that set is the union of the shards' centroid bitmaps
+            params = DeviceIndex.with_subset_flag(params)
+            cbitmap = idx.shard_subset_begin(q16, params, subset)
+            keys = idx.shard_subset_keys(all_gather(cbitmap), int(q16.shape[1]), params)
+        all_keys = all_gather(keys)
         # step 2: exact scores of the globally surviving documents only, all-gather of the records
         rec = idx.shard_exact_records(all_keys, rank, int(q16.shape[1]), params)
-        gathered = torch.empty((world,) + tuple(rec.shape), dtype=torch.uint8, device=idx.device)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), rec.view(-1))
-        else:
-            gathered.copy_(rec.unsqueeze(0))
-        ids, scores, counts = idx.merge_records(gathered, params.top_k)
+        ids, scores, counts = idx.merge_records(all_gather(rec), params.top_k)
         return _results_to_lists(ids.cpu(), scores.cpu(), counts.cpu())
 
     @torch.inference_mode()

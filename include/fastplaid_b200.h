@@ -206,6 +206,20 @@ int fpb_merge_shards(const fpb_record* d_all_records /* [n_shards, B, R] */, int
 int fpb_shard_approx_keys(const fpb_index* index, const void* d_queries, int B, int Q,
                           const fpb_params* params, void* d_workspace, size_t workspace_bytes,
                           uint64_t* d_keys /* [B, R] */, void* stream);
+/* Step 1 with a `subset` (search.rs:493-515, :544-551).  The reference restricts probing to the centroids
+ * that the subset documents touch; with the documents sharded that set is the UNION over the shards:
+ *   1a. fpb_shard_subset_begin : centroid scores + this shard's document bitmap and centroid bitmap;
+ *                                copies the centroid bitmap ([B, layout.cbitmap_words] uint32) out
+ *   1b. all-gather of the bitmaps; fpb_shard_subset_keys ORs them, probes, and continues like
+ *       fpb_shard_approx_keys.  Subset ids are GLOBAL document ids (ids outside this shard are ignored).
+ * params->flags must contain FPB_FLAG_SUBSET in both calls and in the later steps' layout. */
+int fpb_shard_subset_begin(const fpb_index* index, const void* d_queries, int B, int Q,
+                           const fpb_params* params, const int32_t* d_subset_ids,
+                           const int64_t* d_subset_offsets, int64_t max_subset_len, void* d_workspace,
+                           size_t workspace_bytes, uint32_t* d_cbitmap_out, void* stream);
+int fpb_shard_subset_keys(const fpb_index* index, int B, int Q, const fpb_params* params, void* d_workspace,
+                          size_t workspace_bytes, const uint32_t* d_all_cbitmaps /* [n_shards, B, words] */,
+                          int n_shards, uint64_t* d_keys /* [B, R] */, void* stream);
 int fpb_shard_apply_threshold(const fpb_index* index, const uint64_t* d_all_keys /* [n_shards, B, R] */,
                               int n_shards, int shard_rank, int B, int Q, const fpb_params* params,
                               void* d_workspace, size_t workspace_bytes, void* stream);

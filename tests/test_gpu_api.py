@@ -153,3 +153,43 @@ def test_two_shards_on_one_gpu_equal_the_unsharded_search(cuda_device):
             torch.cuda.synchronize()
             assert torch.equal(i3, ids) and torch.equal(s3, scores) and torch.equal(c3, counts)
             assert n_scored <= queries.shape[0] * (n_full // 4)  # exact-scored docs: at most R per query in total
+
+
+def test_sharded_subset_search_equals_the_unsharded_subset_search(cuda_device):
+    """subset= with documents sharded: the centroid bitmaps of the shards are OR-ed (the all-gather is
+    emulated by stacking, all shards live on one device) and the result must equal the single-index
+    subset search bit for bit, including a subset that lives entirely in one shard and an empty one."""
+    from fast_plaid_b200.engine import DeviceIndex, shard_tensors
+
+    docs = make_docs(900, 10, 60, seed=31)
+    oidx, _ = build_oracle_index(docs)
+    t = to_index_tensors(oidx)
+    whole = DeviceIndex(t, cuda_device)
+    queries = make_queries(5, 32, seed=32, docs=docs).half().to(cuda_device)
+    g = torch.Generator().manual_seed(33)
+    subset = [torch.randperm(900, generator=g)[:300].tolist(),
+              list(range(0, 200)),                      # only in the first shard(s)
+              [],                                       # empty: no result
+              torch.randperm(900, generator=g)[:40].tolist(),
+              list(range(880, 900)) + [5, 5, 7]]        # duplicates, both ends
+    for n_full, top_k in ((64, 10), (4096, 50)):
+        params = DeviceIndex.make_params(top_k, n_full, 8)
+        ids, scores, counts = whole.search(queries, params, subset=subset)
+        for world in (2, 3):
+            shards = []
+            for r in range(world):
+                sh, base = shard_tensors(t, r, world)
+                shards.append(DeviceIndex(sh, cuda_device, doc_id_base=base))
+            ps = DeviceIndex.with_subset_flag(params)
+            Q = int(queries.shape[1])
+            cbs = torch.stack([d.shard_subset_begin(queries, ps, subset) for d in shards])
+            all_keys = torch.stack([d.shard_subset_keys(cbs, Q, ps) for d in shards])
+            recs = [d.shard_exact_records(all_keys, r, Q, ps) for r, d in enumerate(shards)]
+            i2, s2, c2 = whole.merge_records(torch.stack(recs), top_k)
+            torch.cuda.synchronize()
+            assert torch.equal(c2, counts), (world, n_full, c2.tolist(), counts.tolist())
+            assert int(c2[2]) == 0
+            for b in range(queries.shape[0]):
+                n = int(counts[b])
+                assert torch.equal(i2[b, :n], ids[b, :n]) and torch.equal(s2[b, :n], scores[b, :n]), (world, n_full, b)
+                assert set(i2[b, :n].tolist()) <= set(subset[b])

@@ -62,6 +62,25 @@ def _worker(rank: int, world: int, port: int, out):
         i3, s3, c3 = mine.merge_records(gathered, top_k)
         torch.cuda.synchronize()
         ok = ok and torch.equal(i3, ids) and torch.equal(s3, scores) and torch.equal(c3, counts)
+        # subset search: the shards' centroid bitmaps are all-gathered and OR-ed (search.rs:494-517)
+        g = torch.Generator().manual_seed(5)
+        subset = [torch.randperm(700, generator=g)[:200].tolist() for _ in range(queries.shape[0])]
+        subset[1] = list(range(0, 100))  # lives in shard 0 only
+        i4, s4, c4 = whole.search(queries, params, subset=subset)
+        ps = DeviceIndex.with_subset_flag(params)
+        cb = mine.shard_subset_begin(queries, ps, subset)
+        all_cb = torch.empty((world,) + tuple(cb.shape), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_cb.view(-1), cb.view(-1))
+        keys = mine.shard_subset_keys(all_cb, int(queries.shape[1]), ps)
+        dist.all_gather_into_tensor(all_keys.view(-1), keys.view(-1))
+        rec3 = mine.shard_exact_records(all_keys, rank, int(queries.shape[1]), ps)
+        dist.all_gather_into_tensor(gathered.view(-1), rec3.view(-1))
+        i5, s5, c5 = mine.merge_records(gathered, top_k)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(c5, c4)
+        for b in range(queries.shape[0]):
+            n = int(c4[b])
+            ok = ok and torch.equal(i5[b, :n], i4[b, :n]) and torch.equal(s5[b, :n], s4[b, :n])
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
