@@ -13,8 +13,10 @@
 // UTMALDG): one elected thread arms the stage's mbarrier with the byte count and issues two
 // 64-column boxes; rows past K are zero-filled by the TMA unit.
 //
-// grid = (token tiles, centroid splits); warps 0-3 epilogue (TMEM lanes 32w..), warp 4 TMA
-// producer, warp 8 issues the MMAs.
+// grid = (token tiles, centroid splits); warps 0-7 epilogue (TMEM lane quarter w % 4, column half
+// w / 4 of the 128-centroid tile), warp 8 issues the MMAs, warp 9 is the TMA producer.  (With four
+// epilogue warps the epilogue -- 128 conversions + stores per thread and tile -- was the critical
+// path: 0.33 ms.)
 #include <cuda.h>
 #include <string.h>
 
@@ -22,7 +24,8 @@
 
 namespace {
 
-constexpr int G1_THREADS = 288;
+constexpr int G1_THREADS = 320;
+constexpr int G1_PRODUCER_WARP = 9;
 constexpr int G1_STAGES = 3;
 constexpr int G1_KBLOCK = 128 * 128;      // bytes: 128 rows x 128 B
 constexpr int G1_TILE = 2 * G1_KBLOCK;    // 32 KB operand tile (K = 128)
@@ -34,7 +37,8 @@ struct G1Smem {
   static constexpr int b_off = G1_TILE;
   static constexpr int st_off = b_off + G1_STAGES * G1_TILE;
   static constexpr int bar_off = st_off + 2 * G1_STAGING;
-  static constexpr int bytes = bar_off + 256 + 1024;
+  static constexpr int pmax_off = bar_off + 256;               // fp32 [128] partial tile maxima of the upper half
+  static constexpr int bytes = pmax_off + 512 + 1024;
 };
 
 __device__ __forceinline__ void g1_mbar_init(uint32_t bar, uint32_t count) {
@@ -103,6 +107,7 @@ k1_centroid_v2_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const _
   unsigned char* smS = base + G1Smem::st_off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + G1Smem::bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* pmax = reinterpret_cast<float*>(base + G1Smem::pmax_off);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3);
   const uint32_t bar_tfull = smem_u32(bars + 6), bar_tempty = smem_u32(bars + 8);
 
@@ -128,7 +133,7 @@ k1_centroid_v2_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const _
     }
     for (int t = 0; t < 2; ++t) {
       g1_mbar_init(bar_tfull + 8 * t, 1);
-      g1_mbar_init(bar_tempty + 8 * t, 4);
+      g1_mbar_init(bar_tempty + 8 * t, 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,7 +148,7 @@ k1_centroid_v2_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const _
   const uint32_t tmem_base = *tmem_slot;
   const int n_my = ct_end - ct_begin;
 
-  if (warp == 4) {
+  if (warp == G1_PRODUCER_WARP) {
     // =========================== TMA producer: centroid tiles -> swizzled smem ===========================
     if (lane == 0) {
       for (int i = 0; i < n_my; ++i) {
@@ -188,9 +193,10 @@ k1_centroid_v2_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const _
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
+  } else if (warp < 8) {
     // =========================== epilogue ===========================
-    const int trow = warp * 32 + lane;           // token row inside the tile == TMEM lane
+    const int quarter = warp & 3, half = warp >> 2;  // TMEM lanes 32*quarter.., columns 64*half..
+    const int trow = quarter * 32 + lane;        // token row inside the tile == TMEM lane
     const int tok = tt * 128 + trow;
     const bool tok_valid = tok < n_tokens;
     const int b = tok / Qp, q = tok % Qp;
@@ -205,15 +211,15 @@ k1_centroid_v2_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const _
       unsigned char* stg = smS + sb * G1_STAGING;
       // the bulk stores issued from this staging buffer two tiles ago must have finished reading it
       if (tid < n_blk) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       g1_mbar_wait(bar_tfull + 8 * acc, (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float mx = -INFINITY;
       unsigned char* my = stg + blk * blk_bytes + q * 2;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
         uint32_t r[32];
-        g1_tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + acc * 128 + c0, r);
+        g1_tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + acc * 128 + c0, r);
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           const float f = __uint_as_float(r[x]);
@@ -224,9 +230,11 @@ k1_centroid_v2_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const _
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) g1_mbar_arrive(bar_tempty + 8 * acc);
-      if (tok_valid) tmax[(int64_t(b) * Qp + q) * n_ctiles + ct] = __float2half_rn(mx);
+      if (half == 1) pmax[trow] = mx;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && tok_valid)
+        tmax[(int64_t(b) * Qp + q) * n_ctiles + ct] = __float2half_rn(fmaxf(mx, pmax[trow]));
       if (tid < n_blk) {
         const int bb = (tt * 128) / Qp + tid;    // query of block `tid`
         if (bb < B) {
