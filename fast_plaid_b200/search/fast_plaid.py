@@ -63,13 +63,11 @@ def save_list_tensors_on_disk(path: str, tensors: list[torch.Tensor]) -> None:
 
 
 def _results_to_lists(ids: torch.Tensor, scores: torch.Tensor, counts: torch.Tensor) -> list[list[tuple[int, float]]]:
-    """Re-zip of search_on_device (fast_plaid.py:247-253)."""
-    ids_l = ids.tolist()
-    sc_l = scores.tolist()
-    out = []
-    for b, n in enumerate(counts.tolist()):
-        out.append(list(zip(ids_l[b][:n], sc_l[b][:n])))
-    return out
+    """Re-zip of search_on_device (fast_plaid.py:247-253): per query the first `count` (id, score) pairs.
+    One flat zip and B list slices: the 6 400 tuples of a 64 x 100 result are the dominant host cost."""
+    k = int(ids.shape[1]) if ids.dim() == 2 else 0
+    flat = list(zip(ids.reshape(-1).tolist(), scores.reshape(-1).tolist()))
+    return [flat[b * k : b * k + n] for b, n in enumerate(counts.tolist())]
 
 
 class FastPlaid:
