@@ -291,6 +291,39 @@ def shard_tensors(data: IndexTensors, rank: int, world: int) -> tuple[IndexTenso
     return shard, lo
 
 
+# Host -> device upload of the big index arrays (the loader fast path; the reference goes
+# through pageable `.to(device)` copies after materialising int64 codes, load.py:35-322).  Arrays above
+# UPLOAD_DIRECT_BYTES are streamed through two pinned staging buffers: the CPU pass that narrows the
+# dtype (int64 codes -> int32) writes straight into pinned memory while the previous chunk's DMA runs.
+UPLOAD_DIRECT_BYTES = 256 << 20
+UPLOAD_CHUNK_BYTES = 64 << 20
+
+
+def upload_narrow(src: torch.Tensor, device: torch.device, dtype: torch.dtype) -> torch.Tensor:
+    """src (host, any integer/float dtype, contiguous in dim 0) -> new device tensor of `dtype`."""
+    src = src if src.is_contiguous() else src.contiguous()
+    out_bytes = src.numel() * torch.empty((), dtype=dtype).element_size()
+    if src.device.type != "cpu" or out_bytes <= UPLOAD_DIRECT_BYTES or src.dim() == 0 or src.shape[0] == 0:
+        return src.to(device, dtype).contiguous()
+    out = torch.empty(src.shape, dtype=dtype, device=device)
+    row_bytes = max(1, out_bytes // src.shape[0])
+    rows = max(1, UPLOAD_CHUNK_BYTES // row_bytes)
+    stage = [torch.empty((rows,) + tuple(src.shape[1:]), dtype=dtype).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    copy_stream = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(copy_stream):
+        for i, r0 in enumerate(range(0, src.shape[0], rows)):
+            r1 = min(src.shape[0], r0 + rows)
+            slot = i & 1
+            if i >= 2:
+                done[slot].synchronize()  # the DMA that last read this staging buffer has finished
+            stage[slot][: r1 - r0].copy_(src[r0:r1])  # dtype narrowing + copy into pinned memory, one pass
+            out[r0:r1].copy_(stage[slot][: r1 - r0], non_blocking=True)
+            done[slot].record(copy_stream)
+    copy_stream.synchronize()
+    return out
+
+
 class DeviceIndex:
     """One index (or shard) resident in HBM + its ``fpb_index`` handle."""
 
@@ -318,8 +351,8 @@ class DeviceIndex:
             self.num_tokens = int(offs[-1])
             self.doc_offsets = offs.to(dev)
             # rows past the last document (the reference's tail padding, load.py:298-300) are dropped
-            self.doc_codes = data.doc_codes[: self.num_tokens].to(dev, torch.int32).contiguous()
-            self.doc_residuals = data.doc_residuals[: self.num_tokens].to(dev, torch.uint8).contiguous()
+            self.doc_codes = upload_narrow(data.doc_codes[: self.num_tokens], dev, torch.int32)
+            self.doc_residuals = upload_narrow(data.doc_residuals[: self.num_tokens], dev, torch.uint8)
             if self.doc_codes.numel() == 0:
                 self.doc_codes = torch.zeros(1, dtype=torch.int32, device=dev)
                 self.doc_residuals = torch.zeros((1, self.dim * self.nbits // 8), dtype=torch.uint8, device=dev)
@@ -331,7 +364,7 @@ class DeviceIndex:
                 io = torch.zeros(il.shape[0] + 1, dtype=torch.int64)
                 io[1:] = il.cumsum(0)
                 self.ivf_offsets = io.to(dev)
-                self.ivf_pids = data.ivf.to(dev, torch.int32).contiguous()
+                self.ivf_pids = upload_narrow(data.ivf, dev, torch.int32)
                 if self.ivf_pids.numel() == 0:
                     self.ivf_pids = torch.zeros(1, dtype=torch.int32, device=dev)
                 n_ivf = int(io[-1])

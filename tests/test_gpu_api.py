@@ -193,3 +193,32 @@ def test_sharded_subset_search_equals_the_unsharded_subset_search(cuda_device):
                 n = int(counts[b])
                 assert torch.equal(i2[b, :n], ids[b, :n]) and torch.equal(s2[b, :n], scores[b, :n]), (world, n_full, b)
                 assert set(i2[b, :n].tolist()) <= set(subset[b])
+
+
+def test_chunked_pinned_upload_equals_the_direct_copy(cuda_device, monkeypatch):
+    """Loader fast path: arrays above the threshold stream through two pinned staging buffers with the
+    int64 -> int32 narrowing done while copying into pinned memory; contents must equal `.to()`."""
+    from fast_plaid_b200 import engine
+
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(0, 2**31 - 1, (100_003,), generator=g, dtype=torch.int64)
+    res = torch.randint(0, 256, (50_001, 64), generator=g, dtype=torch.uint8)
+    monkeypatch.setattr(engine, "UPLOAD_DIRECT_BYTES", 1024)
+    monkeypatch.setattr(engine, "UPLOAD_CHUNK_BYTES", 37 * 1024)  # many chunks, ragged last chunk
+    dev = torch.device(cuda_device)
+    a = engine.upload_narrow(codes, dev, torch.int32)
+    b = engine.upload_narrow(res, dev, torch.uint8)
+    assert a.dtype == torch.int32 and torch.equal(a.cpu(), codes.to(torch.int32))
+    assert b.dtype == torch.uint8 and torch.equal(b.cpu(), res)
+    # a whole index built through the chunked path searches identically
+    docs = make_docs(300, 10, 40, seed=5)
+    oidx, _ = build_oracle_index(docs)
+    t = to_index_tensors(oidx)
+    q = make_queries(3, 32, seed=6, docs=docs).half().to(cuda_device)
+    p = engine.DeviceIndex.make_params(10, 128, 8)
+    chunked = engine.DeviceIndex(t, cuda_device)
+    monkeypatch.setattr(engine, "UPLOAD_DIRECT_BYTES", 1 << 40)
+    direct = engine.DeviceIndex(t, cuda_device)
+    r1, r2 = chunked.search(q, p), direct.search(q, p)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(r1, r2))
