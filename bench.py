@@ -76,6 +76,8 @@ class ClockSampler:
         self.thread: threading.Thread | None = None
 
     def start(self) -> None:
+        if os.environ.get("FPB_BENCH_NO_SAMPLER"):  # diagnosis only: measure the sampler's own perturbation
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -314,10 +316,9 @@ def run_b200(args) -> dict:
         if world == 1:
             # fp32 host queries -> fp16 cast into pinned staging -> H2D + search + D2H inside the C-ABI call
             return _results_to_lists(*didx.search_host(qb_host, params))
-        q16 = qb_host.to(torch.float16)  # the reference casts on the host (fast_plaid.py:241)
         import torch.distributed as dist
 
-        qd = q16.pin_memory().to(device, non_blocking=True)
+        qd = didx.stage_queries(qb_host, k)  # host fp32 -> fp16 cast into pinned memory (fast_plaid.py:241) + H2D
         kk = didx.shard_approx_keys(qd, params)
         dist.all_gather_into_tensor(all_keys.view(-1), kk.view(-1))
         r = didx.shard_exact_records(all_keys, rank, Q, params)

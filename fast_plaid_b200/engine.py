@@ -110,6 +110,8 @@ EXPORTED_SYMBOLS = [
     "fpb_reconstruct",
     "fpb_token_scores",
     "fpb_encode",
+    "fpb_cast_f32_to_f16_host",
+    "fpb_cast_f32_to_f16_host_portable",
 ]
 
 
@@ -181,6 +183,10 @@ def load_library() -> ctypes.CDLL:
         lib.fpb_merge_shards.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
         lib.fpb_reconstruct.restype = i32
         lib.fpb_reconstruct.argtypes = [vp, vp, i32, vp, vp, vp]
+        for name in ("fpb_cast_f32_to_f16_host", "fpb_cast_f32_to_f16_host_portable"):
+            fn = getattr(lib, name)
+            fn.restype = i32
+            fn.argtypes = [vp, vp, sz]
         lib.fpb_encode.restype = i32
         lib.fpb_encode.argtypes = [i32, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp]
         lib.fpb_token_scores.restype = i32
@@ -517,25 +523,14 @@ class DeviceIndex:
                     self._keepalive = (sid, soff)  # until the stream has consumed them
         return ids, scores, counts
 
-    def search_host(
-        self, queries_host: torch.Tensor, params: FpbParams
-    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """queries_host: fp16 [B, Q, D] in (preferably pinned) HOST memory.  The H2D copy, the
-        search and the D2H copies of the results all happen inside the C-ABI call, which
-        synchronises the stream.  Returns HOST tensors (ids, scores, counts)."""
-        if queries_host.dim() != 3:
-            raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries_host.shape)}")
-        if queries_host.device.type != "cpu" or not queries_host.dtype.is_floating_point:
-            raise ValueError("search_host expects floating-point queries in host memory")
-        B, Q, D = queries_host.shape
-        if D != self.dim:
-            raise ValueError(f"query dim {D} != index dim {self.dim}")
-        k = params.top_k
+    def _host_io(self, B: int, Q: int, k: int) -> dict[str, torch.Tensor]:
+        """Cached pinned + device staging buffers of the host-buffer path."""
         key = (B, Q, k)
         with self._lock:
             io = self._io.get(key)
             if io is None:
                 self._io.clear()
+                D = self.dim
                 io = {
                     "d_q": torch.empty((B, Q, D), dtype=torch.float16, device=self.device),
                     "d_ids": torch.empty((B, k), dtype=torch.int64, device=self.device),
@@ -547,10 +542,41 @@ class DeviceIndex:
                     "h_counts": torch.empty((B,), dtype=torch.int32).pin_memory(),
                 }
                 self._io[key] = io
+        return io
+
+    def _cast_into_pinned(self, queries_host: torch.Tensor, h_q: torch.Tensor) -> None:
+        """fp32 -> fp16 on the host like the reference (fast_plaid.py:241), straight into pinned memory."""
+        if queries_host.dtype == torch.float32 and queries_host.is_contiguous():
+            # single-threaded F16C cast in the library: no dependence on ATen's intra-op pool (csrc/host_cast.cu)
+            _check(self._lib.fpb_cast_f32_to_f16_host(queries_host.data_ptr(), h_q.data_ptr(), queries_host.numel()))
+        else:
+            h_q.copy_(queries_host)
+
+    def stage_queries(self, queries_host: torch.Tensor, top_k: int) -> torch.Tensor:
+        """Host queries [B, Q, D] -> fp16 device tensor (cached buffer; asynchronous on the current stream)."""
+        B, Q, _ = queries_host.shape
+        io = self._host_io(B, Q, top_k)
+        self._cast_into_pinned(queries_host, io["h_q"])
+        io["d_q"].copy_(io["h_q"], non_blocking=True)
+        return io["d_q"]
+
+    def search_host(
+        self, queries_host: torch.Tensor, params: FpbParams
+    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """queries_host: float [B, Q, D] in HOST memory.  The H2D copy, the search and the D2H copies of the
+        results all happen inside the C-ABI call, which synchronises the stream.  Returns HOST tensors
+        (ids, scores, counts) that are reused by the next call of the same shape."""
+        if queries_host.dim() != 3:
+            raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries_host.shape)}")
+        if queries_host.device.type != "cpu" or not queries_host.dtype.is_floating_point:
+            raise ValueError("search_host expects floating-point queries in host memory")
+        B, Q, D = queries_host.shape
+        if D != self.dim:
+            raise ValueError(f"query dim {D} != index dim {self.dim}")
+        io = self._host_io(B, Q, params.top_k)
         if B == 0:
             return io["h_ids"], io["h_scores"], io["h_counts"]
-        # one pass: cast to fp16 (fast_plaid.py:241 does the cast on the host too) into pinned memory
-        io["h_q"].copy_(queries_host)
+        self._cast_into_pinned(queries_host, io["h_q"])
         queries_host = io["h_q"]
         step = self.max_queries_per_call(Q, params)
         with torch.cuda.device(self.device):

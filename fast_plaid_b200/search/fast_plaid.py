@@ -451,7 +451,10 @@ class FastPlaid:
                 out.copy_(t.unsqueeze(0))
             return out
 
-        q16 = queries.to(device=idx.device, dtype=torch.float16, non_blocking=True)
+        if queries.device.type == "cpu" and queries.dtype.is_floating_point:
+            q16 = idx.stage_queries(queries, params.top_k)  # host cast (fast_plaid.py:241) + async H2D
+        else:
+            q16 = queries.to(device=idx.device, dtype=torch.float16, non_blocking=True)
         rank, world = self.shard
         # step 1: local pruning, all-gather of the approximate-score keys
         if subset is None:

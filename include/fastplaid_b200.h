@@ -242,6 +242,12 @@ int fpb_token_scores(const fpb_index* index, const void* d_queries, int Q, const
  * (bucketize right=false + LSB-first bits + big-endian packbits, create.rs:413-427, :176-184).
  *   d_tokens f16 [n_tokens, dim], d_centroids f16 [n_centroids, dim], d_cutoffs f32 [(1<<nbits)-1]
  *   d_codes i32 [n_tokens], d_residuals u8 [n_tokens, dim*nbits/8] */
+/* Host utility: round-to-nearest-even fp32 -> fp16 cast of a query batch (the cast search_on_device does
+ * on the host, fast_plaid.py:241), single-threaded with F16C.  The _portable variant is the same
+ * conversion in plain C, exported so the tests can compare the two. */
+int fpb_cast_f32_to_f16_host(const float* h_src, void* h_dst, size_t n);
+int fpb_cast_f32_to_f16_host_portable(const float* h_src, void* h_dst, size_t n);
+
 int fpb_encode(int device, int nbits, int dim, int64_t n_centroids, const void* d_centroids,
                const void* d_tokens, int64_t n_tokens, const float* d_cutoffs, int32_t* d_codes,
                uint8_t* d_residuals, void* stream);

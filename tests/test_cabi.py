@@ -72,3 +72,26 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle"
                 assert "plaid_oracle" not in src and "index_oracle" not in src, f"{f} mentions the oracle modules"
+
+
+def test_host_cast_equals_the_aten_cast():
+    """fpb_cast_f32_to_f16_host (F16C) and its portable twin reproduce torch's fp32 -> fp16 cast bit for bit:
+    random values over the whole exponent range, every fp16 rounding midpoint and its two neighbours,
+    subnormals, overflow to inf, signed zeros, inf, NaN."""
+    lib = engine.load_library()
+    g = torch.Generator().manual_seed(0)
+    h = torch.arange(0, 0x7C00, dtype=torch.int16).view(torch.float16).float()
+    mid = (h[:-1] + h[1:]) / 2
+    inf = torch.tensor(float("inf"))
+    x = torch.cat([
+        torch.randn(50_000, generator=g), torch.randn(20_000, generator=g) * 1e-5, torch.randn(20_000, generator=g) * 1e4,
+        torch.randn(20_000, generator=g) * 1e-7, mid, -mid, torch.nextafter(mid, inf), torch.nextafter(mid, -inf),
+        torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 65504.0, 65519.9, 65520.0, 65536.0, 1e-8,
+                      2.9802322e-8, 2.98e-8, 5.96e-8, 6.0975552e-05, 6.1e-5]),
+    ]).contiguous()
+    ref = x.to(torch.float16)
+    for fn in (lib.fpb_cast_f32_to_f16_host, lib.fpb_cast_f32_to_f16_host_portable):
+        out = torch.empty(x.shape, dtype=torch.float16)
+        assert fn(x.data_ptr(), out.data_ptr(), x.numel()) == 0
+        same = (out.view(torch.int16) == ref.view(torch.int16)) | (torch.isnan(out) & torch.isnan(ref))
+        assert bool(same.all()), int((~same).sum())
