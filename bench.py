@@ -385,7 +385,7 @@ def run_b200(args) -> dict:
         },
         "e2e": {"value": B * args.steps / (e2e_ms / 1000.0), "unit": "queries/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "path": "fp32 host queries -> fp16 cast on host -> fpb_search_batch_host (H2D, search, D2H, sync) -> "
+                "path": "fp32 host queries -> fp16 cast on the host (fpb_cast_f32_to_f16_host) -> fpb_search_batch_host (H2D, search, D2H, sync) -> "
                         "Python list[list[(doc_id, score)]]"},
         "gpu_launches": (10 if world == 1 else 13) * args.steps,
         "clocks": clocks,
