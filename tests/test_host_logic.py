@@ -122,3 +122,27 @@ def test_k_heuristic():
     assert num_partitions_for(100_000 * 300) == 65536
     assert num_partitions_for(1_000_000 * 300) == 262144
     assert num_partitions_for(50_000 * 1024) == 65536
+
+
+def test_result_lists_c_helper_equals_the_python_zip():
+    """csrc/py/results.c builds the list[list[(int, float)]] results; it must equal the pure-Python re-zip
+    (types included) for full, partial and empty rows, and leave the garbage collector enabled."""
+    import gc
+
+    from fast_plaid_b200.search import fast_plaid as fp
+
+    assert fp._fpb_results is not None, "the CPython helper was not built (make -C fast_plaid_b200/csrc)"
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(-5, 10**9, (7, 13), generator=g)
+    sc = torch.randn(7, 13, generator=g)
+    cnt = torch.tensor([13, 0, 5, 13, 1, 12, 7], dtype=torch.int32)
+    a = fp._results_to_lists(ids, sc, cnt)
+    helper, fp._fpb_results = fp._fpb_results, None
+    try:
+        b = fp._results_to_lists(ids, sc, cnt)
+    finally:
+        fp._fpb_results = helper
+    assert a == b and [len(r) for r in a] == cnt.tolist()
+    assert all(type(i) is int and type(s) is float for r in a for i, s in r)
+    assert gc.isenabled()
+    assert fp._results_to_lists(torch.empty((0, 4), dtype=torch.int64), torch.empty((0, 4)), torch.empty(0, dtype=torch.int32)) == []
