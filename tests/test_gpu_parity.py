@@ -348,3 +348,25 @@ def test_empty_document_gets_the_reference_score(cuda_device):
             assert ids[b, int(counts[b]) - 1] == 7
     emb = didx.reconstruct([7, 8])
     assert emb[0].shape[0] == 0 and emb[1].shape[0] == int(lens[8])
+
+
+def test_select_fallback_path_with_all_equal_scores(cuda_device):
+    """An all-zero query gives S == 0 everywhere, so every candidate has the same approximate score: the value
+    range is empty, the bucket fast path of k3b_select declines and the radix passes must pick, by the canonical
+    rule, the n_full_scores/4 smallest candidate ids.  The exact scores are all 0 too: ids come back ascending."""
+    from fast_plaid_b200.engine import DeviceIndex
+
+    oidx, didx, _, _, _ = _setup("base", cuda_device)
+    q = torch.zeros(2, 32, 128, dtype=torch.float16, device=cuda_device)
+    params = DeviceIndex.make_params(16, 64, 8)  # R = 16 documents re-ranked, far fewer than the candidates
+    st = didx.run_stages(q, params)
+    torch.cuda.synchronize()
+    for b in range(2):
+        n = int(st["n_cand"][b])
+        assert n > 16
+        assert bool((st["approx"][b, :n] == 0).all())
+        cand = st["cand"][b, :n].cpu()
+        assert torch.equal(st["rerank"][b, :16].cpu(), cand[:16])  # candidates are in ascending id order
+        ids = st["ids"][b, : int(st["counts"][b])].cpu()
+        assert torch.equal(ids, torch.sort(ids).values) and int(st["counts"][b]) == 16
+        assert bool((st["scores"][b, :16] == 0).all())
