@@ -7,8 +7,9 @@
 // one candidate document: 32 codes are read with one coalesced load, each S row (Qp fp16 =
 // LPR x 16 B) is fetched by LPR adjacent lanes so a warp-wide load touches 32/LPR distinct
 // rows (one L1 wavefront per row instead of four), and the running maxima stay in registers.
-// The stage is bound by L2 gather bandwidth (Qp*2 bytes per token per query); the codes
-// stream from HBM once per (query, candidate).
+// The stage is bound by the L1 data pipe (one wavefront per gathered row; 97 % busy at Qp = 32) or, at
+// Qp = 64, by L2 bandwidth; the codes stream from HBM once per (query, candidate).  Two kernels: the
+// shuffle-free one below (default up to Qp = 32) and this one (Qp >= 64, unaligned code arrays).
 #include <stdlib.h>
 
 #include "kernels.h"

@@ -1,4 +1,6 @@
 // K5 v2 : fused residual decompression + exact MaxSim for (dim=128, nbits=4, Qp in {32,64}).
+// Superseded as the default by v4 (Qp <= 32) and v5 (Qp > 32); still the path for Qp = 64 indexes whose
+// longest document does not fit v5's pass table, and the A/B reference (FPB_K5=v2).
 // Same arithmetic, bit for bit, as k5_maxsim.cu (v1, kept for the other shapes); what changed
 // is the data movement, guided by the round-1 ncu capture (profiles/r01_summary.md: v1 was
 // bound by L1/shared wavefronts at 75 % and issued only 35 % of its slots):
