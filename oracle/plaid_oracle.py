@@ -252,7 +252,9 @@ def search_one(
     """One query [Q, D] (any float dtype; cast to fp16 as fast_plaid.py:241 does).
 
     ``inject`` lets a test substitute a stage output computed elsewhere (e.g. the GPU's
-    centroid-score table ``S``) to check that everything downstream of it is bit-exact.
+    centroid-score table ``S``) to check that everything downstream of it is bit-exact;
+    ``inject["subset_centroids"]`` replaces the centroid set derived from the subset documents
+    (the document-sharded engine uses the union over the shards, tests/test_sharding.py).
     Returns (passage_ids: list[int], scores: list[float]) or, with ``return_stages``, a
     dict that also holds every intermediate.
     """
@@ -276,10 +278,13 @@ def search_one(
     if subset is not None:  # :494-517
         subset = subset.to(torch.int64)
         subset_codes, _ = ragged_lookup(index.doc_codes, index.doc_offsets, index.doc_lengths, subset)
-        if subset_codes.numel() == 0:
+        uniq_c = torch.unique(subset_codes.flatten(), sorted=True)
+        st["subset_centroids"] = uniq_c
+        if "subset_centroids" in inject:
+            uniq_c = inject["subset_centroids"].to(torch.int64)
+        if uniq_c.numel() == 0:
             flat_cells = torch.empty(0, dtype=torch.int64)
         else:
-            uniq_c = torch.unique(subset_codes.flatten(), sorted=True)
             sub_scores = S.index_select(0, uniq_c)
             actual_k = min(n_ivf_probe, uniq_c.shape[0])
             local = _topk_rows_per_column(sub_scores, actual_k, ties)

@@ -116,3 +116,45 @@ def test_world_size_2_gloo_all_gather():
         ref_ids, ref_sc = po.search_one(queries[b], oidx, N_PROBE, 2000, N_FULL, TOP_K, ties="canonical")
         assert [d for d, _ in results[b]] == ref_ids
         assert [float(s) for _, s in results[b]] == pytest.approx(ref_sc, abs=0)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_subset_search_equals_single_index(world):
+    """subset= with sharded documents (search.rs:494-517 restricts the probe to the centroids the subset
+    documents touch): each shard derives that set from its own subset documents, the sets are united (the
+    engine all-gathers and ORs bitmaps), every shard probes with the union and masks its candidates with its
+    local subset; global prune + rank as before.  Must equal the unsharded subset search exactly."""
+    oidx, queries = _fixture()
+    g = torch.Generator().manual_seed(9)
+    n_docs = int(oidx.doc_lengths.shape[0])
+    subsets = [torch.randperm(n_docs, generator=g)[:80], torch.arange(0, 50), torch.arange(n_docs - 30, n_docs)]
+    R = N_FULL // 4
+    shards = [_shard_oracle(oidx, r, world) for r in range(world)]
+    for b in range(queries.shape[0]):
+        sub = subsets[b]
+        ref_ids, ref_sc = po.search_one(queries[b], oidx, N_PROBE, 2000, N_FULL, TOP_K, subset=sub, ties="canonical")
+        assert len(ref_ids) > 0
+        local = []
+        for sh, base in shards:
+            n_local = int(sh.doc_lengths.shape[0])
+            m = (sub >= base) & (sub < base + n_local)
+            local.append(sub[m] - base)
+        # step 1a on every shard: the centroids its own subset documents touch
+        sets = []
+        for (sh, _), ls in zip(shards, local):
+            st = po.search_one(queries[b], sh, N_PROBE, 2000, N_FULL, 10**9, subset=ls, ties="canonical", return_stages=True)
+            sets.append(st["subset_centroids"])
+        union = torch.unique(torch.cat(sets), sorted=True)
+        # step 1b..: probe with the union, candidates masked by the local subset, records, global merge
+        recs = []
+        for (sh, base), ls in zip(shards, local):
+            st = po.search_one(queries[b], sh, N_PROBE, 2000, N_FULL, 10**9, subset=ls, ties="canonical",
+                               return_stages=True, inject={"subset_centroids": union})
+            if "rerank" not in st:
+                continue
+            approx_of = dict(zip(st["candidates"].tolist(), st["approx"].tolist()))
+            recs += [(approx_of[d], float(e), d + base) for d, e in zip(st["rerank"].tolist(), st["exact"].tolist())]
+        got = merge_records_host(recs, R, TOP_K)
+        assert [d for d, _ in got] == ref_ids
+        assert [s for _, s in got] == ref_sc
+        assert set(ref_ids) <= set(sub.tolist())
