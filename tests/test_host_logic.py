@@ -146,3 +146,37 @@ def test_result_lists_c_helper_equals_the_python_zip():
     assert all(type(i) is int and type(s) is float for r in a for i, s in r)
     assert gc.isenabled()
     assert fp._results_to_lists(torch.empty((0, 4), dtype=torch.int64), torch.empty((0, 4)), torch.empty(0, dtype=torch.int32)) == []
+
+
+def test_device_list_resolution():
+    """fast_plaid.py:350-362: one string, a list, bare "cuda" -> cuda:0, duplicates dropped in order;
+    anything else is refused like parse_device (load.rs:16-37)."""
+    from fast_plaid_b200.search.fast_plaid import FastPlaid
+
+    r = FastPlaid._resolve_devices
+    assert r("cpu") == ["cpu"]
+    assert r("cuda") == ["cuda:0"]
+    assert r(["cuda:1", "cuda", "cuda:1", "cuda:0"]) == ["cuda:1", "cuda:0"]
+    assert r(None) in (["cpu"], [f"cuda:{i}" for i in range(torch.cuda.device_count())])
+    for bad in ("gpu", "cuda:x", "cuda:", "xpu:0"):
+        with pytest.raises(ValueError):
+            r(bad)
+
+
+def test_query_padding_and_subset_broadcasting():
+    """fast_plaid.py:772-793: a list of [Q_i, D] / [1, Q_i, D] tensors is zero-padded to the longest; `subset`
+    may be one id, one shared list, one list per query, or empty (= no filter); a wrong length is an error."""
+    from fast_plaid_b200.search.fast_plaid import FastPlaid
+
+    a, b = torch.ones(3, 4), torch.full((1, 5, 4), 2.0)
+    q = FastPlaid._as_query_tensor([a, b])
+    assert q.shape == (2, 5, 4) and bool((q[0, 3:] == 0).all()) and bool((q[1] == 2).all())
+    t = torch.zeros(2, 3, 4)
+    assert FastPlaid._as_query_tensor(t) is t
+    s = FastPlaid._per_query_subsets
+    assert s(None, 3) is None and s([], 3) is None
+    assert s(7, 2) == [[7], [7]]
+    assert s([1, 2], 3) == [[1, 2]] * 3
+    assert s([[1], [2, 3]], 2) == [[1], [2, 3]]
+    with pytest.raises(ValueError, match="Subset length must match number of queries"):
+        s([[1], [2]], 3)
