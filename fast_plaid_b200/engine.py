@@ -529,7 +529,8 @@ class DeviceIndex:
         with self._lock:
             io = self._io.get(key)
             if io is None:
-                self._io.clear()
+                while len(self._io) >= 4:  # a few shapes stay cached (pinning memory costs milliseconds)
+                    self._io.pop(next(iter(self._io)))
                 D = self.dim
                 io = {
                     "d_q": torch.empty((B, Q, D), dtype=torch.float16, device=self.device),
