@@ -202,6 +202,10 @@ def run_b200(args) -> dict:
     torch.cuda.synchronize()
     t_index = time.time() - t0
     params = DeviceIndex.make_params(cfg["top_k"], N_FULL, N_IVF_PROBE)
+    if args.approx == "direct":  # A/B: one-pass approximate stage (every row of every candidate gathered)
+        from fast_plaid_b200.engine import FPB_FLAG_APPROX_DIRECT
+
+        params = DeviceIndex.with_flags(params, FPB_FLAG_APPROX_DIRECT)
     B, Q = cfg["B"], cfg["Q"]
 
     # queries: rank 0 makes them from its shard, everybody gets the same ones
@@ -288,6 +292,7 @@ def run_b200(args) -> dict:
         one_step(q_dev16[w % N_QUERY_BATCHES], None)
     barrier()
 
+    didx.views(buf, lay)["stats"].zero_()  # counters of the approximate stage: timed steps only
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -310,6 +315,8 @@ def run_b200(args) -> dict:
     ms_bytes = maxsim_algorithmic_bytes(didx, views, lay)
     ap_hbm, ap_gather = approx_algorithmic_bytes(didx, views, lay)
     n_cand_mean = float(views["n_cand"].float().mean())
+    k3_stats = [int(x) for x in views["stats"].cpu().tolist()]
+    n_refine_mean = float(views["n_refine"].float().mean()) if args.approx != "direct" else None
 
     # ---- e2e: host fp32 queries in -> Python lists out, copies inside the timed region ----
     def e2e_call(qb_host: torch.Tensor):
@@ -395,7 +402,13 @@ def run_b200(args) -> dict:
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ms_bytes, "launch_ms": stage_ms[i_ms]},
         "stages_ms": dict(zip(stage_names, [round(x, 4) for x in stage_ms])),
-        "approx_stage": {"hbm_bytes_per_launch": ap_hbm, "l2_gather_bytes_per_launch": ap_gather,
+        "approx_stage": {"mode": args.approx,
+                         # two-pass: rows gathered by the bound pass / tokens it walked, and by the exact pass
+                         "bound_pass_rows_per_token": (k3_stats[0] / k3_stats[1]) if k3_stats[1] else None,
+                         "exact_pass_rows_per_token": (k3_stats[2] / k3_stats[1]) if k3_stats[1] else None,
+                         "rows_gathered_per_step": (k3_stats[0] + k3_stats[2]) / args.steps,
+                         "refined_candidates_per_query_mean": n_refine_mean,
+                         "hbm_bytes_per_launch": ap_hbm, "l2_gather_bytes_per_launch": ap_gather,
                          "hbm_gbs": ap_hbm / (stage_ms[i_ap] / 1000.0) / 1e9 if stage_ms[i_ap] > 0 else None,
                          "l2_gather_gbs": ap_gather / (stage_ms[i_ap] / 1000.0) / 1e9 if stage_ms[i_ap] > 0 else None},
         "wall_s_timed_region": round(t_wall, 3),
@@ -609,6 +622,8 @@ def main() -> None:
     ap.add_argument("--config", choices=list(CONFIGS), default="cfg3")
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries timed on the CPU (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--approx", choices=["two-pass", "direct"], default="two-pass",
+                    help="approximate stage: exact two-pass pruning (default) or the one-pass A/B alternative")
     args = ap.parse_args()
     # keep stdout clean for the ONE JSON line: NCCL / libraries may print to fd 1
     sys.stdout.flush()

@@ -289,11 +289,8 @@ extern "C" int fpb_encode(int device, int nbits, int dim, int64_t n_centroids, c
     fpb_set_error("fpb_encode: cuTensorMapEncodeTiled failed");
     return FPB_ERR_CUDA;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(encode_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EnSmem::bytes));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(encode_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EnSmem::bytes));
   cudaDeviceProp prop;
   FPB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   const int64_t n_ttiles = (n_tokens + 127) / 128;

@@ -47,7 +47,7 @@ void fpb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* fpb_last_error(void) { return g_err; }
-extern "C" int fpb_abi_version(void) { return 3; }  // 3: fpb_shard_subset_begin / fpb_shard_subset_keys
+extern "C" int fpb_abi_version(void) { return 4; }  // 4: two-pass approximate stage (layout fields, FPB_FLAG_APPROX_*)
 
 static int bitrev(int x, int nbits) {
   int r = 0;
@@ -200,6 +200,18 @@ extern "C" int fpb_workspace_layout(const fpb_index* ix, int B, int Q, const fpb
   L->off_clist = take(sub ? int64_t(B) * ix->K * 4 : 0);
   L->off_n_clist = take(sub ? int64_t(B) * 4 : 0);
   L->off_sbitmap = take(sub ? int64_t(B) * L->bitmap_words * 4 : 0);
+  // two-pass approximate stage (k3_approx.cu); hb_words is a multiple of 4 so a query's bitmap is uint4-copyable
+  const bool direct = (p->flags & FPB_FLAG_APPROX_DIRECT) != 0;
+  L->hb_words = int(((ix->K + 31) / 32 + 3) / 4 * 4);
+  L->off_tau = take(direct ? 0 : int64_t(B) * Qp * 2);
+  L->off_hibits = take(direct ? 0 : int64_t(B) * L->hb_words * 4);
+  L->off_lb = take(direct ? 0 : int64_t(B) * L->cand_cap * 4);
+  L->off_refine = take(direct ? 0 : int64_t(B) * L->cand_cap * 4);
+  L->off_n_refine = take(int64_t(B) * 4);
+  L->off_thresh = take(int64_t(B) * 4);
+  L->off_work2 = take(int64_t(B + 8) * 4);
+  L->off_stats = take(8 * 8);
+  L->flags = p->flags;
   L->total_bytes = off;
   return FPB_OK;
 }

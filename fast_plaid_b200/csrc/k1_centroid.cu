@@ -267,11 +267,8 @@ int launch_k1_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   auto kern = k1_centroid_scores_kernel<D, QC>;
   constexpr int smem = K1Smem<D, QC>::bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   // split the batch over gridDim.y only when the centroid tiles alone cannot fill the chip
   int ysplit = 1;
   const int want = 2 * ix->sm_count;

@@ -265,11 +265,8 @@ int launch_centroid_scores_v2(const fpb_index* ix, const Ws& ws, cudaStream_t st
   const fpb_layout& L = *ws.L;
   if (ix->dim != 128 || L.Qp > 128 || !ix->has_tmap) return FPB_OK;
   *handled = true;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(k1_centroid_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G1Smem::bytes));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(k1_centroid_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G1Smem::bytes));
   const int n_ttiles = (L.B * L.Qp + 127) / 128;
   const int n_ctiles = L.n_tiles;
   int splits = ix->sm_count / n_ttiles;

@@ -2,14 +2,27 @@
 //         approx[d] = sum_{q<Q}^{fp32}  max_{t<len(d)}  S[b][code[d,t]][q]     (fp16 max)
 // K3b : pruning to the n_full_scores/4 best candidates                     (search.rs:602-619)
 //
-// The reference gathers S rows into a [tokens, Q] tensor, pads it to [2000, maxlen, Q],
-// masks, maxes and sums, 128 times per query with two host syncs each.  Here one warp walks
-// one candidate document: 32 codes are read with one coalesced load, each S row (Qp fp16 =
-// LPR x 16 B) is fetched by LPR adjacent lanes so a warp-wide load touches 32/LPR distinct
-// rows (one L1 wavefront per row instead of four), and the running maxima stay in registers.
-// The stage is bound by the L1 data pipe (one wavefront per gathered row; 97 % busy at Qp = 32) or, at
-// Qp = 64, by L2 bandwidth; the codes stream from HBM once per (query, candidate).  Two kernels: the
-// shuffle-free one below (default up to Qp = 32) and this one (Qp >= 64, unaligned code arrays).
+// The reference gathers S rows into a [tokens, Q] tensor, pads it to [2000, maxlen, Q], masks, maxes and
+// sums, 128 times per query with two host syncs each.  A one-pass GPU formulation (one warp walks one
+// candidate, every token gathers its Qp*2-byte S row) is bound by the L1 data pipe: one wavefront per
+// gathered row, 4.87 G rows per batch on cfg-3 = 16.8 ms at one wavefront per clock per SM, and the kernel
+// sat at 97 % of that (profiles/r01c_k3_approx_nsh_raw.csv).  Going faster needs FEWER ROWS, exactly:
+//
+//   1. tau[b,q]   = a quantile of the per-128-centroid-tile column maxima K1 already produces
+//                   (any value is correct; it only moves work between the two passes)
+//   2. hi[b,c]    = exists q: S[b,c,q] >= tau[b,q]          (a K-bit map per query, in shared memory)
+//   3. bound pass : walk every candidate, test one bit per token, gather ONLY the rows of high centroids
+//                   (~16 % of the tokens at the median tile maximum).  With m_q = max over the gathered rows:
+//                     m_q >= tau_q  =>  m_q is the true column maximum (every skipped row is < tau_q <= m_q)
+//                     otherwise     =>  m_q <= true maximum < tau_q
+//                   so   lb = sum_q m_q  <=  approx  <=  sum_q max(m_q, tau_q) = ub,  with lb == ub == approx
+//                   bit for bit when every column is resolved (fp32 addition is monotone in each operand and
+//                   both sums use the summation order of the exact kernel).
+//   4. threshold  : T = a value such that at least n_full_scores/4 candidates have lb >= T.
+//   5. exact pass : the unresolved candidates with ub >= T are re-scored with all their rows.
+//   A candidate left with an upper bound has approx <= ub < T <= the scores of >= n_full_scores/4 others:
+//   it cannot enter the pruned list whatever the tie rule, and K3b (which only orders by value) never
+//   selects it.  The pruned list and everything after it are bit-identical to scoring every candidate.
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -17,63 +30,114 @@
 namespace {
 
 constexpr int K3_THREADS = 256;
-constexpr int K3_DOCS_PER_CHUNK = 64;
+constexpr int K3_DOCS_PER_CHUNK = 64;    // exact pass: work-queue granule
+constexpr int K3A_DOCS_PER_CHUNK = 128;  // bound pass
+constexpr int K3_WQ = 128;               // bound pass: per-warp ring of high codes waiting for their gather
 
-__global__ void k3_prefix_kernel(const int32_t* __restrict__ n_cand, int B, int32_t* __restrict__ work) {
+// chunk prefix of the dynamic work queue: work[b] = first chunk of query b, work[B] = total, work[B+1] = counter
+__global__ void k3_prefix_kernel(const int32_t* __restrict__ n_items, int B, int per_chunk,
+                                 int32_t* __restrict__ work) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
     for (int b = 0; b < B; ++b) {
       work[b] = acc;
-      acc += (n_cand[b] + K3_DOCS_PER_CHUNK - 1) / K3_DOCS_PER_CHUNK;
+      acc += (n_items[b] + per_chunk - 1) / per_chunk;
     }
     work[B] = acc;
-    work[B + 1] = 0;  // dynamic work counter
+    work[B + 1] = 0;
   }
 }
 
+// next (query, chunk) of the queue; s_b = -1 when it is empty.  Called by every thread of the CTA.
+__device__ __forceinline__ void k3_next_chunk(int32_t* work, int B, int* s_b, int* s_c) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int c = atomicAdd(&work[B + 1], 1);
+    if (c >= work[B]) {
+      *s_b = -1;
+    } else {
+      int lo = 0, hi = B - 1;  // largest b with work[b] <= c
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (work[mid] <= c) lo = mid; else hi = mid - 1;
+      }
+      *s_b = lo;
+      *s_c = c - work[lo];
+    }
+  }
+  __syncthreads();
+}
+
+// maxima of the four half2 registers across the lane groups, then the fp32 sum over the real query tokens
+// (sum_dim_intlist(.., Kind::Float), search.rs:401).  The order of the additions is part of the contract between
+// the bound pass and the exact pass: both call this.
+template <int LPR>
+__device__ __forceinline__ void k3_reduce_groups(__half2& m0, __half2& m1, __half2& m2, __half2& m3) {
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1) {
+    m0 = __hmax2(m0, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m0), off)));
+    m1 = __hmax2(m1, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m1), off)));
+    m2 = __hmax2(m2, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m2), off)));
+    m3 = __hmax2(m3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m3), off)));
+  }
+}
+template <int LPR>
+__device__ __forceinline__ float k3_sum_columns(__half2 m0, __half2 m1, __half2 m2, __half2 m3, int col0, int Q) {
+  float s = 0.f;
+  const float2 f0 = __half22float2(m0), f1 = __half22float2(m1), f2 = __half22float2(m2), f3 = __half22float2(m3);
+  if (col0 + 0 < Q) s += f0.x;
+  if (col0 + 1 < Q) s += f0.y;
+  if (col0 + 2 < Q) s += f1.x;
+  if (col0 + 3 < Q) s += f1.y;
+  if (col0 + 4 < Q) s += f2.x;
+  if (col0 + 5 < Q) s += f2.y;
+  if (col0 + 6 < Q) s += f3.x;
+  if (col0 + 7 < Q) s += f3.y;
+#pragma unroll
+  for (int off = 1; off < LPR; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact pass / one-pass scoring.  One warp walks one candidate; each S row (Qp fp16 = LPR x 16 B) is fetched
+// by LPR adjacent lanes, so a warp-wide load touches 32/LPR distinct rows, and the running maxima stay in
+// registers.  `list` (the bound pass's refine list) selects the candidates; NULL = all of them.
+// Two code-distribution schemes: shuffles (any Qp) or, for Qp <= 32, shuffle-free vector loads of the
+// LPR consecutive codes a lane group gathers (the __shfl_sync run through the same L1 data pipe as the gathers).
+// ---------------------------------------------------------------------------------------
 template <int LPR, int UNROLL, int MINB>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
                  const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
-                 const int32_t* __restrict__ n_cand, int32_t* __restrict__ work, int B,
-                 float* __restrict__ approx) {
+                 const int32_t* __restrict__ n_cand, const int32_t* __restrict__ list,
+                 const int32_t* __restrict__ n_list, int32_t* __restrict__ work, int B,
+                 float* __restrict__ approx, unsigned long long* __restrict__ stats) {
   constexpr int QP = LPR * 8;
   constexpr int TPI = 32 / LPR;
   __shared__ int s_b, s_c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane % LPR, grp = lane / LPR;
   const __half2 sentinel = __float2half2_rn(FPB_PAD_SENTINEL);
+  unsigned long long rows = 0;
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      const int c = atomicAdd(&work[B + 1], 1);
-      if (c >= work[B]) {
-        s_b = -1;
-      } else {
-        int lo = 0, hi = B - 1;  // largest b with work[b] <= c
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (work[mid] <= c) lo = mid; else hi = mid - 1;
-        }
-        s_b = lo;
-        s_c = c - work[lo];
-      }
-    }
-    __syncthreads();
+    k3_next_chunk(work, B, &s_b, &s_c);
     const int b = s_b;
-    if (b < 0) return;
-    const int n = n_cand[b];
+    if (b < 0) break;
+    const int n = list ? n_list[b] : n_cand[b];
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP);
     const int32_t* cb = cand + int64_t(b) * cand_cap;
+    const int32_t* lb = list ? list + int64_t(b) * cand_cap : nullptr;
     float* ab = approx + int64_t(b) * cand_cap;
 
     for (int i = 0; i < K3_DOCS_PER_CHUNK / 8; ++i) {
-      const int idx = s_c * K3_DOCS_PER_CHUNK + i * 8 + warp;
-      if (idx >= n) break;
+      const int j = s_c * K3_DOCS_PER_CHUNK + i * 8 + warp;
+      if (j >= n) break;
+      const int idx = lb ? lb[j] : j;
       const int d = cb[idx];
       const int64_t o0 = doc_offsets[d];
       const int len = int(doc_offsets[d + 1] - o0);
+      rows += unsigned(len);
       __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
       for (int base = 0; base < len; base += 32 * UNROLL) {
         int code[UNROLL];
@@ -85,8 +149,8 @@ k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* 
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-          for (int j = 0; j < LPR; ++j) {
-            const int c = __shfl_sync(0xffffffffu, code[u], j * TPI + grp);
+          for (int jj = 0; jj < LPR; ++jj) {
+            const int c = __shfl_sync(0xffffffffu, code[u], jj * TPI + grp);
             if (c >= 0) {
               const uint4 v = __ldg(Sb + int64_t(c) * LPR + sub);
               m0 = __hmax2(m0, u32_as_half2(v.x));
@@ -97,42 +161,18 @@ k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* 
           }
         }
       }
-#pragma unroll
-      for (int off = LPR; off < 32; off <<= 1) {
-        m0 = __hmax2(m0, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m0), off)));
-        m1 = __hmax2(m1, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m1), off)));
-        m2 = __hmax2(m2, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m2), off)));
-        m3 = __hmax2(m3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m3), off)));
-      }
-      // fp32 sum over the real query tokens (sum_dim_intlist(.., Kind::Float), search.rs:401)
-      const int col0 = sub * 8;
-      float s = 0.f;
-      const float2 f0 = __half22float2(m0), f1 = __half22float2(m1), f2 = __half22float2(m2),
-                   f3 = __half22float2(m3);
-      if (col0 + 0 < Q) s += f0.x;
-      if (col0 + 1 < Q) s += f0.y;
-      if (col0 + 2 < Q) s += f1.x;
-      if (col0 + 3 < Q) s += f1.y;
-      if (col0 + 4 < Q) s += f2.x;
-      if (col0 + 5 < Q) s += f2.y;
-      if (col0 + 6 < Q) s += f3.x;
-      if (col0 + 7 < Q) s += f3.y;
-#pragma unroll
-      for (int off = 1; off < LPR; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      k3_reduce_groups<LPR>(m0, m1, m2, m3);
+      const float s = k3_sum_columns<LPR>(m0, m1, m2, m3, sub * 8, Q);
       if (lane == 0) ab[idx] = s;
     }
   }
+  if (stats && lane == 0 && rows) atomicAdd(stats + 2, rows);
 }
 
-// Shuffle-free variant.  The ncu capture of the kernel above (profiles/r01b_top3_raw.csv) shows the
-// L1TEX data pipe 96.5 % busy: 32.1 M of its 38.6 M wavefronts per SM are the row gathers (one per
-// row, the floor of this formulation) and 6.5 M are the __shfl_sync that hand each code to the LPR
-// lanes fetching its row -- shuffles run through the same pipe.  Here the LPR lanes of a group
-// load "their" LPR consecutive codes themselves with one vector load (the lanes of a group read
-// the same 4*LPR bytes: a broadcast, one wavefront for the warp): the document is walked in
-// 32-token windows aligned to absolute multiples of 32 tokens, so the vector loads are aligned
-// whatever the document offset; tokens outside [o0, o0+len) are masked.  max() is order-free,
-// so the values are bit-identical to the shuffle kernel.
+// Shuffle-free variant: the LPR lanes of a group load "their" LPR consecutive codes themselves with one
+// vector load (the lanes of a group read the same 4*LPR bytes: a broadcast); the document is walked in
+// 32-token windows aligned to absolute multiples of 32 tokens, so the vector loads are aligned whatever the
+// document offset; tokens outside [o0, o0+len) are masked.  max() is order-free: bit-identical values.
 template <int LPR>
 __device__ __forceinline__ void load_codes(int (&c)[LPR], const int32_t* p) {
   if constexpr (LPR == 2) {
@@ -151,44 +191,34 @@ template <int LPR, int UNROLL, int MINB>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
                      const int32_t* __restrict__ codes, int64_t n_codes, const int32_t* __restrict__ cand,
-                     int cand_cap, const int32_t* __restrict__ n_cand, int32_t* __restrict__ work, int B,
-                     float* __restrict__ approx) {
+                     int cand_cap, const int32_t* __restrict__ n_cand, const int32_t* __restrict__ list,
+                     const int32_t* __restrict__ n_list, int32_t* __restrict__ work, int B,
+                     float* __restrict__ approx, unsigned long long* __restrict__ stats) {
   constexpr int QP = LPR * 8;
   __shared__ int s_b, s_c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane % LPR, grp = lane / LPR;
   const __half2 sentinel = __float2half2_rn(FPB_PAD_SENTINEL);
+  unsigned long long rows = 0;
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      const int c = atomicAdd(&work[B + 1], 1);
-      if (c >= work[B]) {
-        s_b = -1;
-      } else {
-        int lo = 0, hi = B - 1;  // largest b with work[b] <= c
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (work[mid] <= c) lo = mid; else hi = mid - 1;
-        }
-        s_b = lo;
-        s_c = c - work[lo];
-      }
-    }
-    __syncthreads();
+    k3_next_chunk(work, B, &s_b, &s_c);
     const int b = s_b;
-    if (b < 0) return;
-    const int n = n_cand[b];
+    if (b < 0) break;
+    const int n = list ? n_list[b] : n_cand[b];
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP) + sub;
     const int32_t* cb = cand + int64_t(b) * cand_cap;
+    const int32_t* lb = list ? list + int64_t(b) * cand_cap : nullptr;
     float* ab = approx + int64_t(b) * cand_cap;
 
     for (int i = 0; i < K3_DOCS_PER_CHUNK / 8; ++i) {
-      const int idx = s_c * K3_DOCS_PER_CHUNK + i * 8 + warp;
-      if (idx >= n) break;
+      const int j = s_c * K3_DOCS_PER_CHUNK + i * 8 + warp;
+      if (j >= n) break;
+      const int idx = lb ? lb[j] : j;
       const int d = cb[idx];
       const int64_t o0 = doc_offsets[d];
       const int len = int(doc_offsets[d + 1] - o0);
+      rows += unsigned(len);
       // frame: token f of the frame is absolute token w0 + f; the document is [lo, hi)
       const int64_t w0 = o0 & ~int64_t(31);
       const int lo = int(o0 - w0), hi = lo + len;
@@ -206,16 +236,16 @@ k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64
             load_codes<LPR>(c[u], cw + fo);
           } else {
 #pragma unroll
-            for (int j = 0; j < LPR; ++j) c[u][j] = (fo + j < readable) ? __ldg(cw + fo + j) : 0;
+            for (int jj = 0; jj < LPR; ++jj) c[u][jj] = (fo + jj < readable) ? __ldg(cw + fo + jj) : 0;
           }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-          for (int j = 0; j < LPR; ++j) {
-            const int f = f0 + u * 32 + grp * LPR + j;
+          for (int jj = 0; jj < LPR; ++jj) {
+            const int f = f0 + u * 32 + grp * LPR + jj;
             if (unsigned(f - lo) < unsigned(len)) {
-              const uint4 v = __ldg(Sb + int64_t(c[u][j]) * LPR);
+              const uint4 v = __ldg(Sb + int64_t(c[u][jj]) * LPR);
               m0 = __hmax2(m0, u32_as_half2(v.x));
               m1 = __hmax2(m1, u32_as_half2(v.y));
               m2 = __hmax2(m2, u32_as_half2(v.z));
@@ -224,29 +254,401 @@ k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64
           }
         }
       }
-#pragma unroll
-      for (int off = LPR; off < 32; off <<= 1) {
-        m0 = __hmax2(m0, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m0), off)));
-        m1 = __hmax2(m1, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m1), off)));
-        m2 = __hmax2(m2, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m2), off)));
-        m3 = __hmax2(m3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m3), off)));
-      }
-      const int col0 = sub * 8;
-      float s = 0.f;
-      const float2 f0 = __half22float2(m0), f1 = __half22float2(m1), f2 = __half22float2(m2),
-                   f3 = __half22float2(m3);
-      if (col0 + 0 < Q) s += f0.x;
-      if (col0 + 1 < Q) s += f0.y;
-      if (col0 + 2 < Q) s += f1.x;
-      if (col0 + 3 < Q) s += f1.y;
-      if (col0 + 4 < Q) s += f2.x;
-      if (col0 + 5 < Q) s += f2.y;
-      if (col0 + 6 < Q) s += f3.x;
-      if (col0 + 7 < Q) s += f3.y;
-#pragma unroll
-      for (int off = 1; off < LPR; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      k3_reduce_groups<LPR>(m0, m1, m2, m3);
+      const float s = k3_sum_columns<LPR>(m0, m1, m2, m3, sub * 8, Q);
       if (lane == 0) ab[idx] = s;
     }
+  }
+  if (stats && lane == 0 && rows) atomicAdd(stats + 2, rows);
+}
+
+// ---------------------------------------------------------------------------------------
+// Two-pass scheme, step 1: tau[b,q] = the `quant`-quantile (from below) of the tile maxima of column (b,q).
+// The tile maxima are the per-128-centroid column maxima K1 writes for the probe; the x-quantile of the
+// maxima of 128-row tiles sits near the x^(1/128)-quantile of the column (median -> top 0.54 %).
+// One CTA per (b, q); 16-bit radix select over at most 4096 (strided) tiles.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k3_tau_kernel(const __half* __restrict__ tmax, int n_tiles, int Q, int Qp, float quant, __half* __restrict__ tau) {
+  __shared__ int hist[256];
+  __shared__ int s_bin, s_rank;
+  const int b = blockIdx.x / Qp, q = blockIdx.x % Qp, tid = threadIdx.x;
+  uint16_t* out = reinterpret_cast<uint16_t*>(tau) + int64_t(b) * Qp + q;
+  if (q >= Q) {  // padded column: never "high", excluded from every sum
+    if (tid == 0) *out = 0x7C00u;  // +inf
+    return;
+  }
+  const uint16_t* tm = reinterpret_cast<const uint16_t*>(tmax) + (int64_t(b) * Qp + q) * n_tiles;
+  const int stride = (n_tiles + 4095) / 4096;
+  const int n = (n_tiles + stride - 1) / stride;
+  int k = int(quant * float(n - 1));  // ascending rank of the selected sample
+  k = max(0, min(n - 1, k));
+  hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) atomicAdd(&hist[f16_key(tm[i * stride]) >> 8], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int cum = 0, bin = 0;
+    for (; bin < 255; ++bin) {
+      if (cum + hist[bin] > k) break;
+      cum += hist[bin];
+    }
+    s_bin = bin;
+    s_rank = k - cum;
+  }
+  __syncthreads();
+  const int hbin = s_bin, rk = s_rank;
+  __syncthreads();
+  hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const uint32_t key = f16_key(tm[i * stride]);
+    if (int(key >> 8) == hbin) atomicAdd(&hist[key & 255u], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int cum = 0, bin = 0;
+    for (; bin < 255; ++bin) {
+      if (cum + hist[bin] > rk) break;
+      cum += hist[bin];
+    }
+    const uint32_t key = (uint32_t(hbin) << 8) | uint32_t(bin);
+    *out = uint16_t((key & 0x8000u) ? (key & 0x7fffu) : (~key & 0xffffu));  // inverse of f16_key
+  }
+}
+
+// step 2: hi[b,c] = exists q: S[b,c,q] >= tau[b,q].  One warp per 32 consecutive centroids = one bitmap word;
+// LPR lanes per row, so every warp-wide load is 512 contiguous bytes of S.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k3_hibits_kernel(const __half* __restrict__ S, int64_t K, const __half* __restrict__ tau,
+                 uint32_t* __restrict__ hibits, int hb_words) {
+  constexpr int QP = LPR * 8, TPI = 32 / LPR;
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int64_t word = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t c0 = word * 32;
+  if (c0 >= K) return;  // warp-uniform
+  const int sub = lane % LPR, grp = lane / LPR;
+  const uint4 t = *reinterpret_cast<const uint4*>(tau + int64_t(b) * QP + sub * 8);
+  const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP);
+  constexpr uint32_t GMASK = (LPR == 32) ? 0xffffffffu : ((1u << (LPR & 31)) - 1u);
+  bool mine = false;
+#pragma unroll
+  for (int j = 0; j < LPR; ++j) {
+    const int64_t c = c0 + j * TPI + grp;
+    bool h = false;
+    if (c < K) {
+      const uint4 v = ldg_nc_na(Sb + c * LPR + sub);
+      const unsigned any = __hge2_mask(u32_as_half2(v.x), u32_as_half2(t.x)) |
+                           __hge2_mask(u32_as_half2(v.y), u32_as_half2(t.y)) |
+                           __hge2_mask(u32_as_half2(v.z), u32_as_half2(t.z)) |
+                           __hge2_mask(u32_as_half2(v.w), u32_as_half2(t.w));
+      h = any != 0u;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, h);
+    // centroid c0 + l (l = this lane) was handled in iteration l / TPI by lane group l % TPI
+    if (lane / TPI == j) mine = ((bal >> ((lane % TPI) * LPR)) & GMASK) != 0u;
+  }
+  const unsigned w = __ballot_sync(0xffffffffu, mine);
+  if (lane == 0) hibits[int64_t(b) * hb_words + word] = w;
+}
+
+// step 3: the bound pass.  Shared memory: the query's K-bit map + one K3_WQ-entry ring of high codes per warp.
+template <int LPR, int MINB>
+__global__ void __launch_bounds__(K3_THREADS, MINB)
+k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
+                const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
+                const int32_t* __restrict__ n_cand, int32_t* __restrict__ work, int B,
+                const __half* __restrict__ tau, const uint32_t* __restrict__ hibits, int hb_words,
+                float* __restrict__ ub_out, float* __restrict__ lb_out, unsigned long long* __restrict__ stats) {
+  constexpr int QP = LPR * 8;
+  constexpr int TPI = 32 / LPR;          // rows per warp-wide gather
+  constexpr int U = (LPR <= 4) ? 4 : 8;  // gathers in flight per lane
+  constexpr int FLUSH = U * TPI;         // rows per flush (<= 64)
+  static_assert(FLUSH + 32 <= K3_WQ, "ring too small");
+  extern __shared__ __align__(16) uint32_t k3_smem[];
+  uint32_t* bm = k3_smem;
+  __shared__ int s_b, s_c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  int32_t* wq = reinterpret_cast<int32_t*>(k3_smem + hb_words) + warp * K3_WQ;
+  unsigned lt_mask;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  const __half2 sentinel = __float2half2_rn(FPB_PAD_SENTINEL);
+  unsigned rows = 0, toks = 0;  // per warp over the CTA's life: far below 2^32
+  int cur_b = -1;
+
+  for (;;) {
+    k3_next_chunk(work, B, &s_b, &s_c);
+    const int b = s_b;
+    if (b < 0) break;
+    if (b != cur_b) {  // CTA-uniform; every warp is past the previous chunk (barrier in k3_next_chunk)
+      const uint4* src = reinterpret_cast<const uint4*>(hibits + int64_t(b) * hb_words);
+      for (int i = tid; i < hb_words / 4; i += K3_THREADS) reinterpret_cast<uint4*>(bm)[i] = src[i];
+      cur_b = b;
+      __syncthreads();
+    }
+    const int n = n_cand[b];
+    const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP) + sub;
+    const int32_t* cb = cand + int64_t(b) * cand_cap;
+    const uint4* tqp = reinterpret_cast<const uint4*>(tau + int64_t(b) * QP + sub * 8);
+
+    for (int i = 0; i < K3A_DOCS_PER_CHUNK / 8; ++i) {
+      const int idx = s_c * K3A_DOCS_PER_CHUNK + i * 8 + warp;
+      if (idx >= n) break;
+      const int d = cb[idx];
+      const int64_t o0 = doc_offsets[d];
+      const int len = int(doc_offsets[d + 1] - o0);
+      // frame aligned to an absolute multiple of 32 tokens: every window is one 128-byte line of codes
+      const int64_t w0 = o0 & ~int64_t(31);
+      const int lo = int(o0 - w0), hi = lo + len;
+      const int32_t* cw = codes + w0 + lane;
+      int head = 0, tail = 0;
+      __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
+      for (int f0 = 0; f0 < hi; f0 += 128) {
+        int c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int f = f0 + u * 32 + lane;
+          c[u] = (f >= lo && f < hi) ? __ldg(cw + f0 + u * 32) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (f0 + u * 32 < hi) {  // warp-uniform
+            const bool bit = c[u] >= 0 && ((bm[c[u] >> 5] >> (c[u] & 31)) & 1u);
+            const unsigned mask = __ballot_sync(0xffffffffu, bit);
+            if (bit) wq[(tail + __popc(mask & lt_mask)) & (K3_WQ - 1)] = c[u];
+            tail += __popc(mask);
+            __syncwarp();
+            while (tail - head >= FLUSH) {
+              uint4 v[U];
+#pragma unroll
+              for (int k = 0; k < U; ++k) {
+                const int code = wq[(head + k * TPI + grp) & (K3_WQ - 1)];
+                v[k] = __ldg(Sb + int64_t(code) * LPR);
+              }
+#pragma unroll
+              for (int k = 0; k < U; ++k) {
+                m0 = __hmax2(m0, u32_as_half2(v[k].x));
+                m1 = __hmax2(m1, u32_as_half2(v[k].y));
+                m2 = __hmax2(m2, u32_as_half2(v[k].z));
+                m3 = __hmax2(m3, u32_as_half2(v[k].w));
+              }
+              head += FLUSH;
+            }
+            __syncwarp();
+          }
+        }
+      }
+      {  // drain: fewer than FLUSH codes left
+        const int rem = tail - head;
+        uint4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int jj = k * TPI + grp;
+          v[k] = make_uint4(half2_as_u32(sentinel), half2_as_u32(sentinel), half2_as_u32(sentinel),
+                            half2_as_u32(sentinel));
+          if (jj < rem) {
+            const int code = wq[(head + jj) & (K3_WQ - 1)];
+            v[k] = __ldg(Sb + int64_t(code) * LPR);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          m0 = __hmax2(m0, u32_as_half2(v[k].x));
+          m1 = __hmax2(m1, u32_as_half2(v[k].y));
+          m2 = __hmax2(m2, u32_as_half2(v[k].z));
+          m3 = __hmax2(m3, u32_as_half2(v[k].w));
+        }
+        __syncwarp();  // the next document's pushes may reuse these slots
+      }
+      rows += unsigned(tail);
+      toks += unsigned(len);
+      k3_reduce_groups<LPR>(m0, m1, m2, m3);
+      // lower bound: the maxima over the gathered rows; upper bound: unresolved columns raised to tau
+      const uint4 tq = __ldg(tqp);
+      const __half2 t0 = u32_as_half2(tq.x), t1 = u32_as_half2(tq.y), t2 = u32_as_half2(tq.z), t3 = u32_as_half2(tq.w);
+      const int col0 = sub * 8;
+      const float lb = k3_sum_columns<LPR>(m0, m1, m2, m3, col0, Q);
+      const float ub = k3_sum_columns<LPR>(__hmax2(m0, t0), __hmax2(m1, t1), __hmax2(m2, t2), __hmax2(m3, t3), col0, Q);
+      // a column is unresolved when its maximum over the gathered rows is below tau (padded columns: tau = +inf,
+      // but they are outside the sums and must not count)
+      const unsigned lt = __hlt2_mask(m0, t0) & ((col0 + 0 < Q ? 0xffffu : 0u) | (col0 + 1 < Q ? 0xffff0000u : 0u));
+      const unsigned lt1 = __hlt2_mask(m1, t1) & ((col0 + 2 < Q ? 0xffffu : 0u) | (col0 + 3 < Q ? 0xffff0000u : 0u));
+      const unsigned lt2 = __hlt2_mask(m2, t2) & ((col0 + 4 < Q ? 0xffffu : 0u) | (col0 + 5 < Q ? 0xffff0000u : 0u));
+      const unsigned lt3 = __hlt2_mask(m3, t3) & ((col0 + 6 < Q ? 0xffffu : 0u) | (col0 + 7 < Q ? 0xffff0000u : 0u));
+      const bool unres = __any_sync(0xffffffffu, (lt | lt1 | lt2 | lt3) != 0u);
+      if (lane == 0) {
+        float l = lb;
+        if (!unres) l = ub;                                            // resolved: ub is the exact score
+        else if (!(l < ub)) l = ub - fabsf(ub) * 1e-6f - 1e-30f;       // keep "unresolved" visible as lb < ub
+        ub_out[int64_t(b) * cand_cap + idx] = ub;
+        lb_out[int64_t(b) * cand_cap + idx] = l;
+      }
+    }
+  }
+  if (stats && lane == 0) {
+    if (rows) atomicAdd(stats + 0, (unsigned long long)rows);
+    if (toks) atomicAdd(stats + 1, (unsigned long long)toks);
+  }
+}
+
+// step 4: per query the pruning threshold T (at least n_dec candidates have lb >= T; found with two levels of
+// 2048 value buckets, so outliers only cost resolution) and the list of unresolved candidates with ub >= T.
+// warp 0: bucket t with count(bucket > t) < need <= count(bucket >= t) over a 2048-bin histogram
+__device__ __forceinline__ void k3_find_bucket(const int* hist, int need, int lane, int* s_t, int* s_need) {
+  int mine = 0;
+  for (int k = 0; k < 64; ++k) mine += hist[lane * 64 + k];
+  int above = 0;
+  for (int l = 31; l >= 0; --l) {
+    const int c = __shfl_sync(0xffffffffu, mine, l);
+    if (l > lane) above += c;
+  }
+  if (above < need && above + mine >= need) {
+    int cum = above, d = lane * 64 + 63;
+    for (; d > lane * 64; --d) {
+      const int h = hist[d];
+      if (cum + h >= need) break;
+      cum += h;
+    }
+    *s_t = d;
+    *s_need = need - cum;  // still to take from bucket d
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+k3_refine_list_kernel(const float* __restrict__ ub, const float* __restrict__ lb, int cand_cap,
+                      const int32_t* __restrict__ n_cand, int n_dec, int refine_all, int32_t* __restrict__ list,
+                      int32_t* __restrict__ n_list, float* __restrict__ thresh) {
+  __shared__ int hist[2048];
+  __shared__ float s_red[64];
+  __shared__ int s_t, s_need, s_cnt;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int n = n_cand[b];
+  const float* ubb = ub + int64_t(b) * cand_cap;
+  const float* lbb = lb + int64_t(b) * cand_cap;
+  int32_t* out = list + int64_t(b) * cand_cap;
+  constexpr int FV = 8;
+  float T = -INFINITY;
+  if (!refine_all && n > n_dec) {  // n <= n_dec: nothing is pruned (search.rs:605 / :615), every score is needed
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i0 = tid; i0 < n; i0 += 1024 * FV) {
+      float v[FV];
+#pragma unroll
+      for (int u = 0; u < FV; ++u) v[u] = (i0 + u * 1024 < n) ? lbb[i0 + u * 1024] : NAN;  // fmin/fmax skip NaN
+#pragma unroll
+      for (int u = 0; u < FV; ++u) {
+        mn = fminf(mn, v[u]);
+        mx = fmaxf(mx, v[u]);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if (lane == 0) {
+      s_red[tid >> 5] = mn;
+      s_red[32 + (tid >> 5)] = mx;
+    }
+    __syncthreads();
+    mn = s_red[lane];
+    mx = s_red[32 + lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    const float range = mx - mn;
+    if (range > 0.f && range < 3.0e38f) {
+      // level 1: 2048 buckets over [mn, mx]; bucket() is monotone in v
+      const float scale1 = 2047.0f / range;
+      auto bucket1 = [&](float v) { return min(2047, max(0, __float2int_rz((v - mn) * scale1))); };
+      for (int i = tid; i < 2048; i += 1024) hist[i] = 0;
+      __syncthreads();
+      for (int i0 = tid; i0 < n; i0 += 1024 * FV) {
+        float v[FV];
+#pragma unroll
+        for (int u = 0; u < FV; ++u) v[u] = (i0 + u * 1024 < n) ? lbb[i0 + u * 1024] : 0.f;
+#pragma unroll
+        for (int u = 0; u < FV; ++u)
+          if (i0 + u * 1024 < n && v[u] == v[u]) atomicAdd(&hist[bucket1(v[u])], 1);
+      }
+      if (tid == 0) s_t = -1;
+      __syncthreads();
+      if (tid < 32) k3_find_bucket(hist, n_dec, lane, &s_t, &s_need);
+      __syncthreads();
+      const int t1 = s_t, need1 = s_need;
+      __syncthreads();
+      if (t1 >= 0) {  // (t1 < 0 only if NaNs leave fewer than n_dec comparable values: T stays -inf)
+        // level 2: 2048 buckets inside bucket t1
+        const float lo1 = mn + float(t1) / scale1;
+        const float scale2 = 2047.0f * scale1;
+        auto bucket2 = [&](float v) { return min(2047, max(0, __float2int_rz((v - lo1) * scale2))); };
+        for (int i = tid; i < 2048; i += 1024) hist[i] = 0;
+        __syncthreads();
+        for (int i0 = tid; i0 < n; i0 += 1024 * FV) {
+          float v[FV];
+#pragma unroll
+          for (int u = 0; u < FV; ++u) v[u] = (i0 + u * 1024 < n) ? lbb[i0 + u * 1024] : 0.f;
+#pragma unroll
+          for (int u = 0; u < FV; ++u)
+            if (i0 + u * 1024 < n && v[u] == v[u] && bucket1(v[u]) == t1) atomicAdd(&hist[bucket2(v[u])], 1);
+        }
+        if (tid == 0) s_t = -1;
+        __syncthreads();
+        if (tid < 32) k3_find_bucket(hist, need1, lane, &s_t, &s_need);
+        __syncthreads();
+        const int t2 = s_t;
+        // T = the smallest value of the selected upper set {b1 > t1} u {b1 == t1, b2 >= t2}: it holds >= n_dec values
+        float tmin = INFINITY;
+        if (t2 >= 0) {
+          for (int i0 = tid; i0 < n; i0 += 1024 * FV) {
+            float v[FV];
+#pragma unroll
+            for (int u = 0; u < FV; ++u) v[u] = (i0 + u * 1024 < n) ? lbb[i0 + u * 1024] : NAN;
+#pragma unroll
+            for (int u = 0; u < FV; ++u) {
+              if (v[u] == v[u]) {
+                const int b1 = bucket1(v[u]);
+                if (b1 > t1 || (b1 == t1 && bucket2(v[u]) >= t2)) tmin = fminf(tmin, v[u]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, off));
+        __syncthreads();
+        if (lane == 0) s_red[tid >> 5] = tmin;
+        __syncthreads();
+        tmin = s_red[lane];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, off));
+        if (t2 >= 0 && tmin < INFINITY) T = tmin;
+      }
+    } else if (range == 0.f) {
+      T = mn;  // every lower bound is the same value: all n > n_dec candidates have lb >= mn
+    }
+  }
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  const int n_up = (n + 1023) / 1024 * 1024;
+  for (int i = tid; i < n_up; i += 1024) {
+    bool take = false;
+    if (i < n) {
+      const float u = ubb[i], l = lbb[i];
+      take = (l < u) && (u >= T);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) out[base + __popc(m & ((1u << lane) - 1u))] = i;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    n_list[b] = s_cnt;
+    thresh[b] = T;
   }
 }
 
@@ -539,68 +941,91 @@ k3b_select_kernel(const float* __restrict__ approx, const int32_t* __restrict__ 
   if (tid == 0) n_rerank[b] = n_dec;
 }
 
+// exact scoring of `list` (NULL: every candidate) into approx
 template <int LPR>
-int launch_k3_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+int launch_k3_exact(const fpb_index* ix, const Ws& ws, const int32_t* list, const int32_t* n_list, int32_t* work,
+                    cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   const int blocks = ix->sm_count * 8;
-  // FPB_K3_VARIANT selects a tuning variant (A/B measurements; all compute identical values)
-  static const int variant = getenv("FPB_K3_VARIANT") ? atoi(getenv("FPB_K3_VARIANT")) : 0;
-#define K3_LAUNCH(U, M)                                                                                     \
-  k3_approx_kernel<LPR, U, M><<<blocks, K3_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets,            \
-                                                             ix->doc_codes, ws.cand(), L.cand_cap, ws.n_cand(), \
-                                                             ws.work(), L.B, ws.approx())
-  // measured on cfg-3 (ms): U1/M6 26.2, U2/M6 20.4, U1/M8 23.5, U2/M8 20.8, U4/M4 22.4
-#define K3_LAUNCH_NSH(U, M)                                                                                  \
-  k3_approx_nsh_kernel<LPR, U, M><<<blocks, K3_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets,         \
-                                                                 ix->doc_codes, ix->E, ws.cand(), L.cand_cap,  \
-                                                                 ws.n_cand(), ws.work(), L.B, ws.approx())
-  if constexpr (LPR <= 8) {
-    // the vector code loads need a 16-byte aligned code array (any torch allocation is)
-    const bool aligned = (reinterpret_cast<uintptr_t>(ix->doc_codes) & 15u) == 0;
-    // default: shuffle-free up to Qp = 32; at Qp = 64 (8 codes per lane) the shuffle kernel is faster
-    // (cfg-5: 10.55 vs 11.31 ms)
-    if (aligned && ((variant == 0 && LPR <= 4) || variant >= 10)) {
-      switch (variant) {
-        case 0: K3_LAUNCH_NSH(2, 6); break;  // default: 20.0-20.2 ms on cfg-3 (shuffle kernel: 20.9-21.0 in the same session)
-        case 10: K3_LAUNCH_NSH(1, 6); break;
-        case 11: K3_LAUNCH_NSH(2, 6); break;
-        case 12: K3_LAUNCH_NSH(2, 5); break;
-        case 13: K3_LAUNCH_NSH(1, 8); break;
-        case 14: K3_LAUNCH_NSH(2, 7); break;
-        case 15: K3_LAUNCH_NSH(2, 8); break;
-        case 16: K3_LAUNCH_NSH(3, 6); break;
-        case 17: K3_LAUNCH_NSH(4, 6); break;
-        default: K3_LAUNCH_NSH(3, 5); break;
-      }
+  if constexpr (LPR <= 4) {
+    // shuffle-free up to Qp = 32 (the vector code loads need a 16-byte aligned code array; any torch allocation
+    // is); at Qp = 64 the shuffle kernel is faster (cfg-5: 10.55 vs 11.31 ms)
+    if ((reinterpret_cast<uintptr_t>(ix->doc_codes) & 15u) == 0) {
+      k3_approx_nsh_kernel<LPR, 2, 6><<<blocks, K3_THREADS, 0, st>>>(
+          ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes, ix->E, ws.cand(), L.cand_cap, ws.n_cand(), list, n_list,
+          work, L.B, ws.approx(), ws.stats());
       FPB_LAUNCH_CHECK("k3_approx_nsh");
       return FPB_OK;
     }
   }
-  switch (variant) {  // shuffle kernel: Qp > 64, unaligned code arrays, or FPB_K3_VARIANT=1..5
-    case 1: K3_LAUNCH(1, 6); break;
-    case 2: K3_LAUNCH(2, 7); break;
-    case 3: K3_LAUNCH(3, 5); break;
-    case 4: K3_LAUNCH(3, 6); break;
-    default: K3_LAUNCH(2, 6); break;  // also FPB_K3_VARIANT=5
-  }
-#undef K3_LAUNCH
-#undef K3_LAUNCH_NSH
+  k3_approx_kernel<LPR, 2, 6><<<blocks, K3_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes,
+                                                             ws.cand(), L.cand_cap, ws.n_cand(), list, n_list, work,
+                                                             L.B, ws.approx(), ws.stats());
   FPB_LAUNCH_CHECK("k3_approx");
   return FPB_OK;
 }
 
+// the quantile of the tile maxima that defines a "high" score; FPB_K3_TAU_Q overrides it (tuning only: every
+// value gives the same results)
+float k3_tau_quantile() {
+  static const float q = [] {
+    const char* e = getenv("FPB_K3_TAU_Q");
+    const float v = e ? float(atof(e)) : 0.5f;
+    return v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+  }();
+  return q;
+}
+
+template <int LPR>
+int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
+  const fpb_layout& L = *ws.L;
+  const size_t smem = size_t(L.hb_words) * 4 + size_t(K3_THREADS / 32) * K3_WQ * 4;
+  // one-pass scoring: asked for, or the K-bit map of a query does not fit next to a second CTA's
+  if ((flags & FPB_FLAG_APPROX_DIRECT) || smem > 100 * 1024) {
+    k3_prefix_kernel<<<1, 32, 0, st>>>(ws.n_cand(), L.B, K3_DOCS_PER_CHUNK, ws.work());
+    FPB_LAUNCH_CHECK("k3_prefix");
+    return launch_k3_exact<LPR>(ix, ws, nullptr, nullptr, ws.work(), st);
+  }
+  k3_tau_kernel<<<L.B * L.Qp, 256, 0, st>>>(ws.tmax(), L.n_tiles, L.Q, L.Qp, k3_tau_quantile(), ws.tau());
+  FPB_LAUNCH_CHECK("k3_tau");
+  {
+    dim3 grid(unsigned((ix->K + 255) / 256), unsigned(L.B));
+    k3_hibits_kernel<LPR><<<grid, 256, 0, st>>>(ws.S(), ix->K, ws.tau(), ws.hibits(), L.hb_words);
+    FPB_LAUNCH_CHECK("k3_hibits");
+  }
+  k3_prefix_kernel<<<1, 32, 0, st>>>(ws.n_cand(), L.B, K3A_DOCS_PER_CHUNK, ws.work());
+  FPB_LAUNCH_CHECK("k3_prefix");
+  {
+    // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)
+    static const int minb = getenv("FPB_K3_MINB") ? atoi(getenv("FPB_K3_MINB")) : 6;  // tuning: 5 (48 regs) or 6 (40)
+    auto kern = minb == 5 ? k3_bound_kernel<LPR, 5> : k3_bound_kernel<LPR, 6>;
+    FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = int((227 * 1024) / (smem + 1024 + 64));
+    per_sm = per_sm < 1 ? 1 : (per_sm > minb ? minb : per_sm);
+    kern<<<ix->sm_count * per_sm, K3_THREADS, smem, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes, ws.cand(),
+                                                          L.cand_cap, ws.n_cand(), ws.work(), L.B, ws.tau(),
+                                                          ws.hibits(), L.hb_words, ws.approx(), ws.lb(), ws.stats());
+    FPB_LAUNCH_CHECK("k3_bound");
+  }
+  k3_refine_list_kernel<<<L.B, 1024, 0, st>>>(ws.approx(), ws.lb(), L.cand_cap, ws.n_cand(), L.R,
+                                              (flags & FPB_FLAG_APPROX_EXACT_ALL) ? 1 : 0, ws.refine(), ws.n_refine(),
+                                              ws.thresh());
+  FPB_LAUNCH_CHECK("k3_refine_list");
+  k3_prefix_kernel<<<1, 32, 0, st>>>(ws.n_refine(), L.B, K3_DOCS_PER_CHUNK, ws.work2());
+  FPB_LAUNCH_CHECK("k3_prefix");
+  return launch_k3_exact<LPR>(ix, ws, ws.refine(), ws.n_refine(), ws.work2(), st);
+}
+
 }  // namespace
 
-int launch_approx(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
+int launch_approx(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
-  k3_prefix_kernel<<<1, 32, 0, st>>>(ws.n_cand(), L.B, ws.work());
-  FPB_LAUNCH_CHECK("k3_prefix");
   switch (L.Qp / 8) {
-    case 2: return launch_k3_t<2>(ix, ws, st);
-    case 4: return launch_k3_t<4>(ix, ws, st);
-    case 8: return launch_k3_t<8>(ix, ws, st);
-    case 16: return launch_k3_t<16>(ix, ws, st);
-    case 32: return launch_k3_t<32>(ix, ws, st);
+    case 2: return launch_k3_t<2>(ix, ws, flags, st);
+    case 4: return launch_k3_t<4>(ix, ws, flags, st);
+    case 8: return launch_k3_t<8>(ix, ws, flags, st);
+    case 16: return launch_k3_t<16>(ix, ws, flags, st);
+    case 32: return launch_k3_t<32>(ix, ws, flags, st);
     default:
       fpb_set_error("approx scoring: unsupported padded query length %d", L.Qp);
       return FPB_ERR_UNSUPPORTED;
@@ -612,11 +1037,8 @@ int launch_select(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   const int Rp2 = fpb_next_pow2(L.R);
   // dynamic keys[] (8 B x Rp2, 32 KB at the maximum R = 4096) on top of 25 KB of static shared memory: opt in
-  static int attr_bytes = 0;
-  if (Rp2 * 8 > attr_bytes) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(k3b_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Rp2 * 8));
-    attr_bytes = Rp2 * 8;
-  }
+  // (per device: cudaFuncSetAttribute applies to the current device only, and the call is cheap)
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(k3b_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Rp2 * 8));
   k3b_select_kernel<<<L.B, 1024, size_t(Rp2) * 8, st>>>(ws.approx(), ws.cand(), L.cand_cap, ws.n_cand(),
                                                        L.R, Rp2, ws.rerank(), ws.rerank_approx(),
                                                        ws.n_rerank());

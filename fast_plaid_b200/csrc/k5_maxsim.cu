@@ -317,11 +317,8 @@ int launch_k5_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   auto kern = k5_maxsim_kernel<D, NBITS, QP>;
   constexpr int smem = K5Smem<D, QP>::bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   WPerm wp;
   for (int i = 0; i < 16; ++i) wp.v[i] = ix->w_perm_bits[i];
   const int64_t items = int64_t(L.B) * L.R;

@@ -231,11 +231,8 @@ int launch_v2_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
   auto kern = k5_maxsim_v2_kernel<QP>;
   constexpr int smem = V2Smem<QP>::bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   WPerm wp;
   for (int i = 0; i < 16; ++i) wp.v[i] = ix->w_perm_bits[i];
   int* counter = ws.work() + L.B + 2;

@@ -410,11 +410,8 @@ int launch_maxsim_v5(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* h
   const fpb_layout& L = *ws.L;
   if (ix->dim != 128 || ix->nbits != 4 || L.Qp > 128) return FPB_OK;
   *handled = true;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(k5_maxsim_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V5Smem::bytes));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(k5_maxsim_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V5Smem::bytes));
   WPerm wp;
   for (int i = 0; i < 16; ++i) wp.v[i] = ix->w_perm_bits[i];
   int* counter = ws.work() + L.B + 3;

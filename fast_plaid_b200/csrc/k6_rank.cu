@@ -271,11 +271,8 @@ int launch_apply_threshold(const Ws& ws, const uint64_t* d_all_keys, int n_shard
     fpb_set_error("apply_threshold: n_shards*R=%d keys per query exceed the shared-memory sort", n_shards * L.R);
     return FPB_ERR_UNSUPPORTED;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(apply_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(apply_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   apply_threshold_kernel<<<L.B, 1024, smem, st>>>(d_all_keys, n_shards, rank, L.B, L.R, P, ws.n_rerank(),
                                                   ws.rerank(), ws.rerank_approx());
   FPB_LAUNCH_CHECK("apply_threshold");
@@ -314,11 +311,8 @@ extern "C" int fpb_merge_shards(const fpb_record* d_all_records, int n_shards, i
     fpb_set_error("fpb_merge_shards: n_shards*R=%d records per query exceed the shared-memory sort", n_shards * R);
     return FPB_ERR_UNSUPPORTED;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    FPB_CUDA_CHECK(cudaFuncSetAttribute(k6_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  FPB_CUDA_CHECK(cudaFuncSetAttribute(k6_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   k6_merge_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(d_all_records, n_shards, B, R, P, Rp2,
                                                                        top_k, d_out_ids, d_out_scores, d_out_counts);
   FPB_LAUNCH_CHECK("k6_merge");

@@ -22,6 +22,14 @@ struct Ws {
   int32_t* clist() const { return reinterpret_cast<int32_t*>(base + L->off_clist); }
   int32_t* n_clist() const { return reinterpret_cast<int32_t*>(base + L->off_n_clist); }
   uint32_t* sbitmap() const { return reinterpret_cast<uint32_t*>(base + L->off_sbitmap); }
+  __half* tau() const { return reinterpret_cast<__half*>(base + L->off_tau); }
+  uint32_t* hibits() const { return reinterpret_cast<uint32_t*>(base + L->off_hibits); }
+  float* lb() const { return reinterpret_cast<float*>(base + L->off_lb); }
+  int32_t* refine() const { return reinterpret_cast<int32_t*>(base + L->off_refine); }
+  int32_t* n_refine() const { return reinterpret_cast<int32_t*>(base + L->off_n_refine); }
+  float* thresh() const { return reinterpret_cast<float*>(base + L->off_thresh); }
+  int32_t* work2() const { return reinterpret_cast<int32_t*>(base + L->off_work2); }
+  unsigned long long* stats() const { return reinterpret_cast<unsigned long long*>(base + L->off_stats); }
 };
 
 int launch_pad_queries(const fpb_index* ix, const Ws& ws, const __half* d_queries, cudaStream_t st);
@@ -37,7 +45,7 @@ int launch_subset(const fpb_index* ix, const Ws& ws, const int32_t* d_ids, const
                   int64_t max_len, cudaStream_t st);                                      // subset structures
 int launch_compact(const uint32_t* bitmap, const uint32_t* mask, int words, int32_t* out, int cap, int32_t* n_out,
                    int B, cudaStream_t st);
-int launch_approx(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3
+int launch_approx(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st); // K3 (flags: FPB_FLAG_APPROX_*)
 int launch_select(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3b
 int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K5 (dispatch)
 int launch_maxsim_v2(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v2 (128/4)

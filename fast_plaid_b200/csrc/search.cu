@@ -48,7 +48,7 @@ int run_until_maxsim(const fpb_index* ix, const Ws& ws, const __half* d_queries,
   if (subset) FPB_TRY(launch_subset(ix, ws, d_subset_ids, d_subset_offsets, max_subset_len, st));
   FPB_TRY(launch_probe(ix, ws, subset, st));
   FPB_TRY(launch_candidates(ix, ws, subset, st));
-  FPB_TRY(launch_approx(ix, ws, st));
+  FPB_TRY(launch_approx(ix, ws, ws.L->flags, st));
   FPB_TRY(launch_select(ix, ws, st));
   FPB_TRY(launch_maxsim(ix, ws, st));
   return FPB_OK;
@@ -149,7 +149,7 @@ extern "C" int fpb_shard_approx_keys(const fpb_index* ix, const void* d_queries,
   FPB_TRY(launch_centroid_scores(ix, ws, st));
   FPB_TRY(launch_probe(ix, ws, false, st));
   FPB_TRY(launch_candidates(ix, ws, false, st));
-  FPB_TRY(launch_approx(ix, ws, st));
+  FPB_TRY(launch_approx(ix, ws, ws.L->flags, st));
   FPB_TRY(launch_select(ix, ws, st));
   return launch_emit_keys(ix, ws, d_keys, st);
 }
@@ -188,7 +188,7 @@ extern "C" int fpb_shard_subset_keys(const fpb_index* ix, int B, int Q, const fp
   FPB_TRY(launch_subset_merge(ix, ws, d_all_cbitmaps, n_shards, st));
   FPB_TRY(launch_probe(ix, ws, true, st));
   FPB_TRY(launch_candidates(ix, ws, true, st));
-  FPB_TRY(launch_approx(ix, ws, st));
+  FPB_TRY(launch_approx(ix, ws, ws.L->flags, st));
   FPB_TRY(launch_select(ix, ws, st));
   return launch_emit_keys(ix, ws, d_keys, st);
 }
@@ -260,7 +260,7 @@ extern "C" int fpb_stage_candidates(const fpb_index* ix, int B, int Q, const fpb
 extern "C" int fpb_stage_approx(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
                                 size_t ws_bytes, void* stream) {
   FPB_STAGE_PROLOGUE(false)
-  return launch_approx(ix, ws, st);
+  return launch_approx(ix, ws, p->flags, st);
 }
 extern "C" int fpb_stage_select(const fpb_index* ix, int B, int Q, const fpb_params* p, void* d_ws,
                                 size_t ws_bytes, void* stream) {

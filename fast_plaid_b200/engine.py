@@ -45,6 +45,8 @@ class FpbParams(ctypes.Structure):
 
 
 FPB_FLAG_SUBSET = 1
+FPB_FLAG_APPROX_EXACT_ALL = 2  # off_approx holds the exact score of every candidate (parity tests)
+FPB_FLAG_APPROX_DIRECT = 4  # one-pass approximate scoring (A/B alternative of the two-pass default)
 
 
 class FpbLayout(ctypes.Structure):
@@ -77,6 +79,16 @@ class FpbLayout(ctypes.Structure):
         ("off_clist", ctypes.c_int64),
         ("off_n_clist", ctypes.c_int64),
         ("off_sbitmap", ctypes.c_int64),
+        ("off_tau", ctypes.c_int64),
+        ("off_hibits", ctypes.c_int64),
+        ("off_lb", ctypes.c_int64),
+        ("off_refine", ctypes.c_int64),
+        ("off_n_refine", ctypes.c_int64),
+        ("off_thresh", ctypes.c_int64),
+        ("off_work2", ctypes.c_int64),
+        ("off_stats", ctypes.c_int64),
+        ("hb_words", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
     ]
 
 
@@ -419,6 +431,11 @@ class DeviceIndex:
         return FpbParams(int(n_ivf_probe), int(n_full_scores), int(top_k), int(batch_size), int(flags))
 
     @staticmethod
+    def with_flags(params: FpbParams, flags: int) -> FpbParams:
+        return FpbParams(params.n_ivf_probe, params.n_full_scores, params.top_k, params.batch_size,
+                         params.flags | int(flags))
+
+    @staticmethod
     def with_subset_flag(params: FpbParams) -> FpbParams:
         return FpbParams(params.n_ivf_probe, params.n_full_scores, params.top_k, params.batch_size,
                          params.flags | FPB_FLAG_SUBSET)
@@ -752,6 +769,16 @@ class DeviceIndex:
             "rerank": v(lay.off_rerank, B * R * 4, torch.int32, (B, R)),
             "rerank_approx": v(lay.off_rerank_approx, B * R * 4, torch.float32, (B, R)),
             "exact": v(lay.off_exact, B * R * 4, torch.float32, (B, R)),
+            # two-pass approximate stage (absent with FPB_FLAG_APPROX_DIRECT)
+            **({} if lay.flags & FPB_FLAG_APPROX_DIRECT else {
+                "tau": v(lay.off_tau, B * Qp * 2, torch.float16, (B, Qp)),
+                "hibits": v(lay.off_hibits, B * lay.hb_words * 4, torch.int32, (B, lay.hb_words)),
+                "approx_lb": v(lay.off_lb, B * lay.cand_cap * 4, torch.float32, (B, lay.cand_cap)),
+                "refine": v(lay.off_refine, B * lay.cand_cap * 4, torch.int32, (B, lay.cand_cap)),
+            }),
+            "n_refine": v(lay.off_n_refine, B * 4, torch.int32, (B,)),
+            "thresh": v(lay.off_thresh, B * 4, torch.float32, (B,)),
+            "stats": v(lay.off_stats, 64, torch.int64, (8,)),
         }
 
     # -- by-products -----------------------------------------------------------------------

@@ -82,6 +82,18 @@ typedef struct fpb_params {
 
 /* The workspace carries the per-query subset structures (search.rs:494-517, :544-547). */
 #define FPB_FLAG_SUBSET 1
+/* Approximate stage (search.rs:554-592).  By default it is computed in two exact passes: a bound pass
+ * that gathers only the score rows of "high" centroids and yields, per candidate, an upper and a lower
+ * bound of its approximate score (equal when the candidate is resolved), then an exact pass over the
+ * unresolved candidates whose upper bound reaches the n_full_scores/4-th best lower bound.  Every
+ * candidate that can enter the pruned list carries its exact score; the others keep an upper bound that
+ * is strictly below the pruning threshold, so the pruned list, its scores and everything after it are
+ * bit-identical to scoring every candidate.
+ *   FPB_FLAG_APPROX_EXACT_ALL : also refine the candidates below the threshold (off_approx then holds
+ *                               the exact score of EVERY candidate; parity tests)
+ *   FPB_FLAG_APPROX_DIRECT    : one-pass scoring of every candidate (the A/B alternative) */
+#define FPB_FLAG_APPROX_EXACT_ALL 2
+#define FPB_FLAG_APPROX_DIRECT 4
 
 /* Byte offsets of every intermediate inside the workspace, so the parity tests can read
  * each stage (S, probed cells, candidates, approx scores, rerank list, exact scores)
@@ -108,6 +120,17 @@ typedef struct fpb_layout {
   int64_t off_clist;     /* i32 [B, K] the same as a sorted list                      */
   int64_t off_n_clist;   /* i32 [B]                                                   */
   int64_t off_sbitmap;   /* u32 [B, bitmap_words] the subset's documents              */
+  /* two-pass approximate stage: */
+  int64_t off_tau;       /* f16 [B, Qp]  per query token the "high" score threshold (+inf on padded columns) */
+  int64_t off_hibits;    /* u32 [B, hb_words] centroid c is high: exists q with S[b,c,q] >= tau[b,q] */
+  int64_t off_lb;        /* f32 [B, cand_cap] lower bound of the approximate score (== off_approx entry when resolved) */
+  int64_t off_refine;    /* i32 [B, cand_cap] candidate indices re-scored exactly by the second pass */
+  int64_t off_n_refine;  /* i32 [B]                                                   */
+  int64_t off_thresh;    /* f32 [B] pruning threshold used by the second pass (-inf: refine all) */
+  int64_t off_work2;     /* i32 [B + 8] chunk prefix + counter of the second pass     */
+  int64_t off_stats;     /* u64 [8] counters: [0] rows gathered by the bound pass, [1] tokens walked by it,
+                            [2] rows gathered by the exact pass (accumulated until the caller clears them) */
+  int32_t hb_words, flags; /* flags = params->flags the layout was made for */
 } fpb_layout;
 
 /* Workspace sizing for a batch of B queries of Q tokens. */

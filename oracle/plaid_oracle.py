@@ -330,6 +330,8 @@ def search_one(
         chunks.append(colbert_score_reduce(padded, mask))  # :583
     approx = torch.cat(chunks, 0)  # :588-592
     st["approx"] = approx
+    if "approx" in inject:  # tests: prune on approximate scores computed elsewhere (same candidate order)
+        approx = inject["approx"].to(torch.float32)
 
     rerank = uniq_pids
     if n_full_scores < approx.shape[0]:  # :605-611

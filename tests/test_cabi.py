@@ -29,13 +29,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(engine.EXPORTED_SYMBOLS) == declared, "engine.EXPORTED_SYMBOLS is out of sync with the header"
-    assert lib.fpb_abi_version() == 3
+    assert lib.fpb_abi_version() == 4
 
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(engine.FpbParams) == 20
-    # 1 int64 + 10 int32 + 17 int64
-    assert ctypes.sizeof(engine.FpbLayout) == 8 + 10 * 4 + 17 * 8
+    # 1 int64 + 10 int32 + 25 int64 + 2 int32
+    assert ctypes.sizeof(engine.FpbLayout) == 8 + 10 * 4 + 25 * 8 + 2 * 4
 
 
 def test_errors_are_reported_not_thrown():

@@ -68,8 +68,22 @@ def test_sample_against_oracle(big, cuda_device):
     oidx = po.OracleIndex(nbits=4, centroids=didx.centroids.cpu(), bucket_weights=didx.bucket_weights.cpu(),
                           ivf=didx.ivf_pids.cpu().long(), ivf_lengths=ivf_len, doc_codes=didx.doc_codes.cpu().long(),
                           doc_residuals=didx.doc_residuals.cpu(), doc_lengths=lens)
-    st = didx.run_stages(queries[:3].half().to(cuda_device), params)
+    from fast_plaid_b200.engine import FPB_FLAG_APPROX_EXACT_ALL, DeviceIndex
+
+    # default two-pass approximate stage first (views of the shared workspace: copy what is compared)
+    dflt = didx.run_stages(queries[:3].half().to(cuda_device), params)
     torch.cuda.synchronize()
+    d_rerank, d_ids, d_scores = dflt["rerank"].clone(), dflt["ids"].clone(), dflt["scores"].clone()
+    d_ub, d_nref = dflt["approx"].clone(), dflt["n_refine"].clone()
+    st = didx.run_stages(queries[:3].half().to(cuda_device), DeviceIndex.with_flags(params, FPB_FLAG_APPROX_EXACT_ALL))
+    torch.cuda.synchronize()
+    for b in range(3):
+        n = int(st["n_cand"][b])
+        # pruned two-pass == every candidate scored exactly: same pruned list and result, upper bounds elsewhere
+        assert torch.equal(d_rerank[b], st["rerank"][b]) and torch.equal(d_ids[b], st["ids"][b])
+        assert torch.equal(d_scores[b], st["scores"][b])
+        assert bool((d_ub[b, :n] >= st["approx"][b, :n]).all())
+        assert int(d_nref[b]) < n // 4, f"query {b}: the exact pass re-scored {int(d_nref[b])} of {n} candidates"
     for b in range(3):
         # integer stages bit-exact given the GPU's S (canonical ties), at 50k+ candidates per query
         S_b = st["S"][b, :, :Q].cpu().contiguous()

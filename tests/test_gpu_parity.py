@@ -48,10 +48,21 @@ def _setup(name: str, device: str):
     queries = make_queries(B, Q, dim=dim, seed=4321, docs=docs if noisy else None)
     params = DeviceIndex.make_params(top_k, n_full, n_probe)
     q16 = queries.to(torch.float16)
-    stages = didx.run_stages(q16.to(device), params)
+    # `stages`: approximate stage with every candidate scored exactly (FPB_FLAG_APPROX_EXACT_ALL), so that
+    # off_approx can be compared entry by entry; the default (pruned two-pass) and the one-pass (DIRECT) runs
+    # are compared with it in test_two_pass_approx_equals_scoring_every_candidate
+    from fast_plaid_b200.engine import FPB_FLAG_APPROX_EXACT_ALL
+
+    stages = _snapshot(didx.run_stages(q16.to(device), DeviceIndex.with_flags(params, FPB_FLAG_APPROX_EXACT_ALL)))
     torch.cuda.synchronize()
     _cache[name] = (oidx, didx, queries, params, stages)
     return _cache[name]
+
+
+def _snapshot(st: dict) -> dict:
+    """run_stages returns views of the (shared, reused) workspace: keep copies."""
+    return {k: (v.clone() if isinstance(v, torch.Tensor) and k != "workspace" else v) for k, v in st.items()
+            if k != "workspace"}
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
@@ -92,11 +103,14 @@ def test_integer_stages_bit_exact_given_S(name, cuda_device):
         assert torch.equal(cand_gpu, ref["candidates"]), f"query {b}: candidate ids differ"
         approx_gpu = st["approx"][b, :n].cpu()
         if not torch.equal(approx_gpu, ref["approx"]):
-            # fp32 sums of fp16 values: exact unless a partial sum needs > 24 bits
+            # fp32 sums of fp16 values: exact unless a partial sum needs > 24 bits (the summation order of
+            # ATen's vectorised sum is not the kernel's).  The pruned list is then checked against the oracle
+            # fed the GPU's own approximate scores.
             rel = ((approx_gpu - ref["approx"]).abs() / ref["approx"].abs().clamp_min(1.0)).max()
             assert float(rel) < 1e-6, f"query {b}: approx scores differ by {float(rel)}"
             n_inexact += 1
-            continue
+            ref = po.search_one(queries[b], oidx, params.n_ivf_probe, 2000, params.n_full_scores, params.top_k,
+                                ties="canonical", return_stages=True, inject={"S": S_b, "approx": approx_gpu})
         r = int(st["n_rerank"][b])
         rer_gpu = st["rerank"][b, :r].cpu().long()
         assert r == ref["rerank"].shape[0]
@@ -104,6 +118,48 @@ def test_integer_stages_bit_exact_given_S(name, cuda_device):
         # id order otherwise -- compare as the oracle produced it
         assert torch.equal(rer_gpu, ref["rerank"]), f"query {b}: pruned list differs"
     assert n_inexact <= B // 2
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_two_pass_approx_equals_scoring_every_candidate(name, cuda_device):
+    """The default approximate stage (bound pass over the rows of high centroids + exact pass over the
+    unresolved candidates that can reach the pruning threshold) must give the same pruned list, the same
+    approximate scores on it, and the same final result as scoring every candidate (EXACT_ALL and the
+    one-pass DIRECT alternative); what it leaves in off_approx for the other candidates is an upper bound
+    strictly below the threshold."""
+    from fast_plaid_b200.engine import FPB_FLAG_APPROX_DIRECT, DeviceIndex
+
+    oidx, didx, queries, params, st = _setup(name, cuda_device)
+    q16 = queries.half().to(cuda_device)
+    direct = _snapshot(didx.run_stages(q16, DeviceIndex.with_flags(params, FPB_FLAG_APPROX_DIRECT)))
+    pruned = _snapshot(didx.run_stages(q16, params))
+    torch.cuda.synchronize()
+    B = queries.shape[0]
+    R = st["layout"].R
+    for b in range(B):
+        n = int(st["n_cand"][b])
+        exact_all = st["approx"][b, :n]
+        assert torch.equal(direct["approx"][b, :n], exact_all), f"query {b}: one-pass and two-pass(all) scores differ"
+        ub = pruned["approx"][b, :n]
+        lb = pruned["approx_lb"][b, :n]
+        T = float(pruned["thresh"][b])
+        assert bool((ub >= exact_all).all()), f"query {b}: an entry of off_approx is below the exact score"
+        refined = torch.zeros(n, dtype=torch.bool, device=ub.device)
+        refined[pruned["refine"][b, : int(pruned["n_refine"][b])].long()] = True
+        resolved = lb == ub  # set by the bound pass; refined entries were overwritten with the exact score
+        known = refined | resolved
+        assert torch.equal(ub[known], exact_all[known]), f"query {b}: a resolved/refined score is not the exact one"
+        assert bool((ub[~known] < T).all()), f"query {b}: an unrefined upper bound reaches the threshold {T}"
+        if n > R:  # at least R candidates are at or above the threshold
+            assert int((exact_all >= T).sum()) >= R
+        for other in (direct, pruned):
+            r = int(st["n_rerank"][b])
+            assert int(other["n_rerank"][b]) == r
+            assert torch.equal(other["rerank"][b, :r], st["rerank"][b, :r]), f"query {b}: pruned lists differ"
+            assert torch.equal(other["rerank_approx"][b, :r], st["rerank_approx"][b, :r])
+            assert torch.equal(other["exact"][b, :r], st["exact"][b, :r])
+        assert torch.equal(pruned["ids"][b], st["ids"][b]) and torch.equal(pruned["scores"][b], st["scores"][b])
+        assert torch.equal(direct["ids"][b], st["ids"][b]) and torch.equal(direct["scores"][b], st["scores"][b])
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
@@ -359,7 +415,7 @@ def test_select_fallback_path_with_all_equal_scores(cuda_device):
     oidx, didx, _, _, _ = _setup("base", cuda_device)
     q = torch.zeros(2, 32, 128, dtype=torch.float16, device=cuda_device)
     params = DeviceIndex.make_params(16, 64, 8)  # R = 16 documents re-ranked, far fewer than the candidates
-    st = didx.run_stages(q, params)
+    st = didx.run_stages(q, params)  # default two-pass approximate stage: tau = 0 = every score, all resolved
     torch.cuda.synchronize()
     for b in range(2):
         n = int(st["n_cand"][b])
