@@ -10,6 +10,7 @@ Reference counterpart: the PyO3 module ``fast_plaid.fast_plaid_rust`` (rust/lib.
 
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import dataclasses
 import os
@@ -223,6 +224,14 @@ def _require_cuda() -> None:
         )
 
 
+def check_supported(dim: int, nbits: int) -> None:
+    """The engine's compiled limits (csrc/index.cu fpb_index_create): raise before an index is written."""
+    if int(nbits) not in (2, 4):
+        raise ValueError(f"unsupported nbits={nbits}: the B200 engine supports nbits 2 and 4")
+    if int(dim) not in (64, 128):
+        raise ValueError(f"unsupported embedding dim={dim}: the B200 engine supports dim 64 and 128")
+
+
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -404,15 +413,37 @@ class DeviceIndex:
         self._buf: torch.Tensor | None = None
         self._io: dict[tuple, dict[str, torch.Tensor]] = {}
         self._lock = threading.Lock()
+        # One search at a time per DeviceIndex: the workspace and the staging buffers are shared, and ctypes
+        # releases the GIL inside the C-ABI call.  (The fpb_index itself is immutable and thread-safe; callers
+        # that want concurrent searches on one GPU give each thread its own workspace through the C ABI.)
+        self._search_lock = threading.RLock()
+        self._last_stream: torch.cuda.Stream | None = None
+
+    @contextlib.contextmanager
+    def _exclusive(self):
+        with self._search_lock:
+            if getattr(self, "_handle", None) is None or not self._handle.value:
+                raise RuntimeError("this DeviceIndex has been closed")
+            st = torch.cuda.current_stream(self.device)
+            if self._last_stream is not None and self._last_stream != st:
+                st.wait_stream(self._last_stream)  # the previous call's kernels still own the workspace
+            self._last_stream = st
+            yield
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
-        if getattr(self, "_handle", None) is not None and self._handle.value:
-            self._lib.fpb_index_destroy(self._handle)
-            self._handle = ctypes.c_void_p()
-        self._ws = {}
-        self._buf = None
-        self._io = {}
+        lock = getattr(self, "_search_lock", None)
+        with (lock if lock is not None else contextlib.nullcontext()):  # wait for a search in flight
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                try:
+                    torch.cuda.synchronize(self.device)  # kernels still reading the index tensors
+                except Exception:
+                    pass
+                self._lib.fpb_index_destroy(self._handle)
+                self._handle = ctypes.c_void_p()
+            self._ws = {}
+            self._buf = None
+            self._io = {}
 
     def __del__(self) -> None:  # pragma: no cover
         try:
@@ -516,7 +547,7 @@ class DeviceIndex:
             params = FpbParams(params.n_ivf_probe, params.n_full_scores, params.top_k, params.batch_size,
                                params.flags | FPB_FLAG_SUBSET)
         step = self.max_queries_per_call(Q, params)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             for s in range(0, B, step):
                 e = min(B, s + step)
                 buf, lay = self.workspace(e - s, Q, params)
@@ -583,7 +614,7 @@ class DeviceIndex:
     ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """queries_host: float [B, Q, D] in HOST memory.  The H2D copy, the search and the D2H copies of the
         results all happen inside the C-ABI call, which synchronises the stream.  Returns HOST tensors
-        (ids, scores, counts) that are reused by the next call of the same shape."""
+        (ids, scores, counts)."""
         if queries_host.dim() != 3:
             raise ValueError(f"Expected a 3D tensor for queries, but got shape {list(queries_host.shape)}")
         if queries_host.device.type != "cpu" or not queries_host.dtype.is_floating_point:
@@ -591,13 +622,15 @@ class DeviceIndex:
         B, Q, D = queries_host.shape
         if D != self.dim:
             raise ValueError(f"query dim {D} != index dim {self.dim}")
-        io = self._host_io(B, Q, params.top_k)
         if B == 0:
-            return io["h_ids"], io["h_scores"], io["h_counts"]
-        self._cast_into_pinned(queries_host, io["h_q"])
-        queries_host = io["h_q"]
+            k = params.top_k
+            return (torch.empty((0, k), dtype=torch.int64), torch.empty((0, k), dtype=torch.float32),
+                    torch.empty((0,), dtype=torch.int32))
         step = self.max_queries_per_call(Q, params)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
+            io = self._host_io(B, Q, params.top_k)
+            self._cast_into_pinned(queries_host, io["h_q"])
+            queries_host = io["h_q"]
             for s in range(0, B, step):
                 e = min(B, s + step)
                 buf, lay = self.workspace(e - s, Q, params)
@@ -610,7 +643,9 @@ class DeviceIndex:
                         io["h_counts"][s:e].data_ptr(), self._stream(),
                     )
                 )
-        return io["h_ids"], io["h_scores"], io["h_counts"]
+            # the pinned result buffers are reused by the next call of this shape: hand out copies (77 KB at
+            # 64 x 100) while this call still owns them
+            return io["h_ids"].clone(), io["h_scores"].clone(), io["h_counts"].clone()
 
     def search_records(self, queries: torch.Tensor, params: FpbParams) -> torch.Tensor:
         """Sharded mode, local half: returns uint8 [B, R, 16] records (approx f32, exact f32,
@@ -619,7 +654,7 @@ class DeviceIndex:
         B, Q, _ = queries.shape
         buf, lay = self.workspace(B, Q, params)
         rec = torch.empty((B, lay.R, 16), dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(
                 self._lib.fpb_search_shard(
                     self._handle, queries.data_ptr(), B, Q, ctypes.byref(params), buf.data_ptr(), buf.numel(),
@@ -634,7 +669,7 @@ class DeviceIndex:
         B, Q, _ = queries.shape
         buf, lay = self.workspace(B, Q, params)
         keys = torch.empty((B, lay.R), dtype=torch.int64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(self._lib.fpb_shard_approx_keys(self._handle, queries.data_ptr(), B, Q, ctypes.byref(params),
                                                    buf.data_ptr(), buf.numel(), keys.data_ptr(), self._stream()))
         return keys
@@ -648,7 +683,7 @@ class DeviceIndex:
         buf, lay = self.workspace(B, Q, params)
         sid, soff, smax = self._subset_csr(subset, 0, B)
         cb = torch.empty((B, lay.cbitmap_words), dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(self._lib.fpb_shard_subset_begin(self._handle, queries.data_ptr(), B, Q, ctypes.byref(params),
                                                     sid.data_ptr(), soff.data_ptr(), smax, buf.data_ptr(),
                                                     buf.numel(), cb.data_ptr(), self._stream()))
@@ -660,7 +695,7 @@ class DeviceIndex:
         n_shards, B, _ = all_cbitmaps.shape
         buf, lay = self.workspace(B, Q, params)
         keys = torch.empty((B, lay.R), dtype=torch.int64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(self._lib.fpb_shard_subset_keys(self._handle, B, Q, ctypes.byref(params), buf.data_ptr(),
                                                    buf.numel(), all_cbitmaps.contiguous().data_ptr(), n_shards,
                                                    keys.data_ptr(), self._stream()))
@@ -672,7 +707,7 @@ class DeviceIndex:
         n_shards, B, R = all_keys.shape
         buf, lay = self.workspace(B, Q, params)
         rec = torch.empty((B, R, 16), dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(self._lib.fpb_shard_apply_threshold(self._handle, all_keys.contiguous().data_ptr(), n_shards, rank,
                                                        B, Q, ctypes.byref(params), buf.data_ptr(), buf.numel(),
                                                        self._stream()))
@@ -688,7 +723,7 @@ class DeviceIndex:
         ids = torch.empty((B, top_k), dtype=torch.int64, device=self.device)
         scores = torch.empty((B, top_k), dtype=torch.float32, device=self.device)
         counts = torch.empty((B,), dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(
                 self._lib.fpb_merge_shards(
                     all_records.contiguous().data_ptr(), n_shards, B, R, top_k, ids.data_ptr(),
@@ -712,7 +747,7 @@ class DeviceIndex:
         st = self._stream()
         p = ctypes.byref(params)
         out: dict[str, Any] = {"layout": lay, "workspace": buf}
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             for name in order:
                 if name == "centroid_scores":
                     _check(self._lib.fpb_stage_centroid_scores(self._handle, queries.data_ptr(), B, Q, p,
@@ -797,7 +832,7 @@ class DeviceIndex:
         out = torch.empty((max(total, 1), self.dim), dtype=torch.float16, device=self.device)
         d_ids = ids.to(self.device, torch.int32)
         d_off = out_off.to(self.device)
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(self._lib.fpb_reconstruct(self._handle, d_ids.data_ptr(), len(doc_ids), d_off.data_ptr(),
                                              out.data_ptr(), self._stream()))
         return [out[int(out_off[i]) : int(out_off[i + 1])] for i in range(len(doc_ids))]
@@ -812,7 +847,7 @@ class DeviceIndex:
             return out[:0]
         qo = query_of.to(self.device, torch.int32).contiguous()
         di = doc_ids.to(self.device, torch.int32).contiguous()
-        with torch.cuda.device(self.device):
+        with self._exclusive(), torch.cuda.device(self.device):
             _check(self._lib.fpb_token_scores(self._handle, queries.data_ptr(), Q, qo.data_ptr(), di.data_ptr(), n,
                                               max(self.max_doc_len, 1), out.data_ptr(), self._stream()))
         return out

@@ -9,8 +9,32 @@ from __future__ import annotations
 
 import json
 import os
+import re
 import sqlite3
+from datetime import date, datetime
 from typing import Any
+
+_IDENT = re.compile(r"^[a-zA-Z_][a-zA-Z0-9_]*$")
+
+
+def _check_column(name: str) -> None:
+    """Column names are interpolated into SQL: only plain identifiers (filtering.py:10-12, :159-165)."""
+    if not isinstance(name, str) or _IDENT.match(name) is None:
+        raise ValueError(
+            f"Invalid column name '{name}'. Column names must start with a letter or underscore, followed by "
+            "letters, digits, or underscores, and cannot contain spaces or special characters."
+        )
+
+
+def _sql_type(value: Any) -> str:
+    """filtering.py:15-25"""
+    if isinstance(value, bool) or isinstance(value, int):
+        return "INTEGER"
+    if isinstance(value, float):
+        return "REAL"
+    if isinstance(value, (datetime, date, str)):
+        return "TEXT"
+    return "BLOB"
 
 
 def _db(index: str) -> str:
@@ -25,8 +49,10 @@ def _insert(conn: sqlite3.Connection, start: int, metadata: list[dict[str, Any]]
     cols = _columns(conn)
     for row in metadata:
         for k in row:
+            _check_column(k)
             if k not in cols:
-                conn.execute(f'ALTER TABLE METADATA ADD COLUMN "{k}"')
+                first = next((r[k] for r in metadata if k in r and r[k] is not None), None)
+                conn.execute(f'ALTER TABLE METADATA ADD COLUMN "{k}" {_sql_type(first)}')
                 cols.append(k)
     for i, row in enumerate(metadata):
         keys = list(row.keys())

@@ -36,29 +36,36 @@ def process_update(fp: Any, docs: list[torch.Tensor], metadata: list[dict] | Non
         return
     n_old = int(meta.get("num_documents", 0))
     emb_path = os.path.join(index_path, "embeddings.npy")
-    if n_old <= start_from_scratch and os.path.exists(emb_path):  # update.py:314-349
-        old = _load_raw(emb_path)
-        if metadata is not None:
-            from ..filtering import update as _meta_update
-
-            _meta_update(index=index_path, metadata=metadata)
-        db = os.path.join(index_path, "metadata.db")
-        keep_db = os.path.exists(db)
-        if keep_db:
-            os.replace(db, db + ".keep")
-        fp.create(old + docs, kmeans_niters=kmeans_niters, max_points_per_centroid=max_points_per_centroid,
-                  nbits=int(meta["nbits"]), n_samples_kmeans=n_samples_kmeans, batch_size=batch_size, seed=seed,
-                  start_from_scratch=start_from_scratch + 1,
-                  compress_only=bool(meta.get("compress_only", False)))
-        if keep_db:
-            os.replace(db + ".keep", db)
-        if len(old) + len(docs) > start_from_scratch and os.path.exists(emb_path):
-            os.remove(emb_path)
-        return
-    if metadata is not None:
+    db = os.path.join(index_path, "metadata.db")
+    if os.path.exists(db):
+        # update.py:300-311: once a metadata table exists EVERY added document gets a row (an empty one when
+        # no metadata is given), so that `_subset_` stays equal to the document id
+        if metadata is None:
+            metadata = [{} for _ in docs]
+        if len(metadata) != len(docs):
+            raise ValueError(
+                f"The length of metadata ({len(metadata)}) must match the number of "
+                f"documents_embeddings ({len(docs)})."
+            )
         from ..filtering import update as _meta_update
 
         _meta_update(index=index_path, metadata=metadata)
+    if n_old <= start_from_scratch and os.path.exists(emb_path):  # update.py:314-349
+        old = _load_raw(emb_path)
+        keep_db = os.path.exists(db)
+        if keep_db:  # create() clears the directory's table: park it
+            os.replace(db, db + ".keep")
+        try:
+            fp.create(old + docs, kmeans_niters=kmeans_niters, max_points_per_centroid=max_points_per_centroid,
+                      nbits=int(meta["nbits"]), n_samples_kmeans=n_samples_kmeans, batch_size=batch_size, seed=seed,
+                      start_from_scratch=start_from_scratch + 1,
+                      compress_only=bool(meta.get("compress_only", False)))
+        finally:
+            if keep_db and os.path.exists(db + ".keep"):
+                os.replace(db + ".keep", db)
+        if len(old) + len(docs) > start_from_scratch and os.path.exists(emb_path):
+            os.remove(emb_path)
+        return
     append_documents(index_path, docs, batch_size=batch_size, device=fp.devices[0])
 
 

@@ -216,10 +216,15 @@ class FastPlaid:
             self.indices = new
             self._last_known_mtime = current
             self._cpu_loaded = True
-        for idx in old.values():
-            if idx is not None:
-                idx.close()
+        self._retire(old)
         return True
+
+    @staticmethod
+    def _retire(old: dict) -> None:
+        """A search thread may still hold a snapshot of the swapped-out handles (`_loaded_indices`): they are not
+        closed here; DeviceIndex.__del__ frees the fpb_index and the HBM when the last reference goes away."""
+        old.clear()
+        gc.collect()
 
     def _swap_in_fresh(self) -> None:
         new = self._load_all()
@@ -228,9 +233,7 @@ class FastPlaid:
             self.indices = new
             self._update_mtime()
             self._cpu_loaded = True
-        for idx in old.values():
-            if idx is not None:
-                idx.close()
+        self._retire(old)
 
     # ------------------------------------------------------------------ create / update / delete
     @staticmethod
@@ -306,6 +309,7 @@ class FastPlaid:
             if num_docs <= start_from_scratch:
                 save_list_tensors_on_disk(os.path.join(self.index, "embeddings.npy"), docs)
             dim = int(docs[0].shape[-1])
+            _engine.check_supported(dim, nbits)  # fail before writing an index the engine cannot search
             primary = self.devices[0]
             centroids = _build.compute_kmeans(
                 docs, dim, primary, kmeans_niters, max_points_per_centroid, seed, n_samples_kmeans

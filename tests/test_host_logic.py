@@ -180,3 +180,37 @@ def test_query_padding_and_subset_broadcasting():
     assert s([[1], [2, 3]], 2) == [[1], [2, 3]]
     with pytest.raises(ValueError, match="Subset length must match number of queries"):
         s([[1], [2]], 3)
+
+
+def test_metadata_rows_follow_document_ids_through_updates(tmp_path):
+    """update.py:300-311 of the reference: once metadata.db exists every update inserts one row per document
+    (an empty one without metadata), so `_subset_` stays the document id."""
+    from fast_plaid_b200 import filtering
+
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    fp.create(make_docs(30, 5, 10, seed=9), kmeans_niters=1, metadata=[{"tag": "old"} for _ in range(30)])
+    fp.update(make_docs(2, 5, 10, seed=10))  # no metadata: two empty rows, ids 30 and 31
+    fp.update(make_docs(1, 5, 10, seed=11), metadata=[{"tag": "new"}])
+    assert filtering.where(path, "tag = ?", ("new",)) == [32]
+    assert len(filtering.get(path)) == 33 == _meta(path)["num_documents"]
+    with pytest.raises(ValueError, match="metadata"):
+        fp.update(make_docs(2, 5, 10, seed=12), metadata=[{"tag": "x"}])
+    assert not os.path.exists(os.path.join(path, "metadata.db.keep"))
+
+
+def test_unsafe_metadata_column_names_are_refused(tmp_path):
+    """filtering.py:10-12, :159-165 of the reference."""
+    fp = search.FastPlaid(str(tmp_path / "idx"), device="cpu")
+    with pytest.raises(ValueError, match="Invalid column name"):
+        fp.create(make_docs(3, 5, 10, seed=13), kmeans_niters=1,
+                  metadata=[{'x" TEXT); DROP TABLE METADATA; --': 1} for _ in range(3)])
+
+
+def test_create_refuses_what_the_engine_cannot_search(tmp_path):
+    fp = search.FastPlaid(str(tmp_path / "idx"), device="cpu")
+    with pytest.raises(ValueError, match="dim"):
+        fp.create(make_docs(5, 5, 10, dim=96, seed=14), kmeans_niters=1)
+    with pytest.raises(ValueError, match="nbits"):
+        fp.create(make_docs(5, 5, 10, seed=14), kmeans_niters=1, nbits=8)
+    assert not os.path.exists(os.path.join(str(tmp_path / "idx"), "metadata.json"))
