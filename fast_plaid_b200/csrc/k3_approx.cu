@@ -263,57 +263,92 @@ k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64
 }
 
 // ---------------------------------------------------------------------------------------
-// Two-pass scheme, step 1: tau[b,q] = the `quant`-quantile (from below) of the tile maxima of column (b,q).
-// The tile maxima are the per-128-centroid column maxima K1 writes for the probe; the x-quantile of the
-// maxima of 128-row tiles sits near the x^(1/128)-quantile of the column (median -> top 0.54 %).
-// One CTA per (b, q); 16-bit radix select over at most 4096 (strided) tiles.
+// Two-pass scheme, step 1: tau[b,q].  Any value is correct; what it should be is decided by the candidates, not by
+// the centroid table: with tau_q at the level that a candidate document holds on average LAMBDA tokens at or above
+// it, a column stays unresolved with probability ~exp(-LAMBDA) and a row is gathered with probability
+// ~Q*LAMBDA/len, whatever the score distribution (uniform codes, clustered topics, short documents).  So tau_q is
+// estimated from a sample: up to K3_TAU_DOCS candidates per query (evenly spaced), every token's S row, and per
+// column the (LAMBDA * #sampled docs)-th largest value, found with a two-level 256-bin radix select on the 16-bit
+// order-preserving keys.  One CTA per query; columns are handled 32 at a time.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k3_tau_kernel(const __half* __restrict__ tmax, int n_tiles, int Q, int Qp, float quant, __half* __restrict__ tau) {
-  __shared__ int hist[256];
-  __shared__ int s_bin, s_rank;
-  const int b = blockIdx.x / Qp, q = blockIdx.x % Qp, tid = threadIdx.x;
-  uint16_t* out = reinterpret_cast<uint16_t*>(tau) + int64_t(b) * Qp + q;
-  if (q >= Q) {  // padded column: never "high", excluded from every sum
-    if (tid == 0) *out = 0x7C00u;  // +inf
-    return;
-  }
-  const uint16_t* tm = reinterpret_cast<const uint16_t*>(tmax) + (int64_t(b) * Qp + q) * n_tiles;
-  const int stride = (n_tiles + 4095) / 4096;
-  const int n = (n_tiles + stride - 1) / stride;
-  int k = int(quant * float(n - 1));  // ascending rank of the selected sample
-  k = max(0, min(n - 1, k));
-  hist[tid] = 0;
-  __syncthreads();
-  for (int i = tid; i < n; i += 256) atomicAdd(&hist[f16_key(tm[i * stride]) >> 8], 1);
-  __syncthreads();
-  if (tid == 0) {
-    int cum = 0, bin = 0;
-    for (; bin < 255; ++bin) {
-      if (cum + hist[bin] > k) break;
-      cum += hist[bin];
+constexpr int K3_TAU_DOCS = 64;
+constexpr int K3_TAU_THREADS = 512;
+
+template <int LPR>
+__global__ void __launch_bounds__(K3_TAU_THREADS)
+k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
+              const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
+              const int32_t* __restrict__ n_cand, float lambda, __half* __restrict__ tau) {
+  constexpr int QP = LPR * 8, TPI = 32 / LPR;
+  constexpr int SUBS = LPR < 4 ? LPR : 4;  // lane subs (8 columns each) handled per round
+  __shared__ int hist[32][256];
+  __shared__ int s_bin[32], s_rem[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  uint16_t* out = reinterpret_cast<uint16_t*>(tau) + int64_t(b) * QP;
+  const int n = n_cand[b];
+  const int ns = min(n, K3_TAU_DOCS);
+  const int32_t* cb = cand + int64_t(b) * cand_cap;
+  const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP);
+  const int want = max(1, __float2int_rn(lambda * float(ns)));  // rank (from the top) of the selected value
+
+  for (int g0 = 0; g0 < LPR; g0 += SUBS) {
+    const bool mine = sub >= g0 && sub < g0 + SUBS;
+    const int qrow = (sub - g0) * 8;  // first of this lane's 8 histogram rows
+    for (int level = 0; level < 2; ++level) {
+      for (int i = tid; i < 32 * 256; i += K3_TAU_THREADS) (&hist[0][0])[i] = 0;
+      __syncthreads();
+      for (int j = warp; j < ns; j += K3_TAU_THREADS / 32) {
+        const int d = cb[int64_t(j) * n / ns];
+        const int64_t o0 = doc_offsets[d];
+        const int len = int(doc_offsets[d + 1] - o0);
+        for (int base = 0; base < len; base += 32) {
+          const int t = base + lane;
+          const int code = (t < len) ? __ldg(codes + o0 + t) : -1;
+#pragma unroll
+          for (int jj = 0; jj < LPR; ++jj) {
+            const int c = __shfl_sync(0xffffffffu, code, jj * TPI + grp);
+            if (c >= 0 && mine) {
+              const uint4 v = __ldg(Sb + int64_t(c) * LPR + sub);
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t key = f16_key(uint16_t(w[e >> 1] >> ((e & 1) * 16)));
+                if (level == 0) {
+                  atomicAdd(&hist[qrow + e][key >> 8], 1);
+                } else if (int(key >> 8) == s_bin[qrow + e]) {
+                  atomicAdd(&hist[qrow + e][key & 255u], 1);
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {  // one thread per column of the round: walk the bins from the top
+        const int need = level == 0 ? want : s_rem[tid];
+        int cum = 0, bin = 255;
+        for (; bin > 0; --bin) {
+          if (cum + hist[tid][bin] >= need) break;
+          cum += hist[tid][bin];
+        }
+        if (level == 0) {
+          s_bin[tid] = bin;
+          s_rem[tid] = need - cum;
+        } else {
+          const int q = g0 * 8 + tid;
+          if (q < QP) {
+            uint32_t key = (uint32_t(s_bin[tid]) << 8) | uint32_t(bin);
+            // fewer sampled values than `want` (tiny documents): everything is "high" -> every column resolves
+            if (s_bin[tid] == 0 && bin == 0) key = f16_key(0xFC00u);  // -inf
+            uint16_t h = uint16_t((key & 0x8000u) ? (key & 0x7fffu) : (~key & 0xffffu));  // inverse of f16_key
+            if (q >= Q) h = 0x7C00u;  // padded column: +inf, never "high", excluded from every sum
+            if (q < QP && tid < SUBS * 8) out[q] = h;
+          }
+        }
+      }
+      __syncthreads();
     }
-    s_bin = bin;
-    s_rank = k - cum;
-  }
-  __syncthreads();
-  const int hbin = s_bin, rk = s_rank;
-  __syncthreads();
-  hist[tid] = 0;
-  __syncthreads();
-  for (int i = tid; i < n; i += 256) {
-    const uint32_t key = f16_key(tm[i * stride]);
-    if (int(key >> 8) == hbin) atomicAdd(&hist[key & 255u], 1);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int cum = 0, bin = 0;
-    for (; bin < 255; ++bin) {
-      if (cum + hist[bin] > rk) break;
-      cum += hist[bin];
-    }
-    const uint32_t key = (uint32_t(hbin) << 8) | uint32_t(bin);
-    *out = uint16_t((key & 0x8000u) ? (key & 0x7fffu) : (~key & 0xffffu));  // inverse of f16_key
   }
 }
 
@@ -353,7 +388,11 @@ k3_hibits_kernel(const __half* __restrict__ S, int64_t K, const __half* __restri
   if (lane == 0) hibits[int64_t(b) * hb_words + word] = w;
 }
 
-// step 3: the bound pass.  Shared memory: the query's K-bit map + one K3_WQ-entry ring of high codes per warp.
+// step 3: the bound pass.  Shared memory: the query's K-bit map, one K3_WQ-entry ring of high codes per warp, and the
+// offsets / lengths of the chunk's documents (staged by the first K3A_DOCS_PER_CHUNK threads so that the dependent
+// candidate -> offset loads are paid once per chunk, not once per document).  A warp walks its documents as a stream
+// of 128-token groups and always has the NEXT group's code loads in flight while it tests, queues and gathers the
+// current one: the pass is otherwise a chain of dependent latencies (codes from HBM, then the gathers from L2).
 template <int LPR, int MINB>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
@@ -365,10 +404,13 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
   constexpr int TPI = 32 / LPR;          // rows per warp-wide gather
   constexpr int U = (LPR <= 4) ? 4 : 8;  // gathers in flight per lane
   constexpr int FLUSH = U * TPI;         // rows per flush (<= 64)
+  constexpr int DPW = K3A_DOCS_PER_CHUNK / (K3_THREADS / 32);  // documents per warp and chunk
   static_assert(FLUSH + 32 <= K3_WQ, "ring too small");
   extern __shared__ __align__(16) uint32_t k3_smem[];
   uint32_t* bm = k3_smem;
   __shared__ int s_b, s_c;
+  __shared__ int64_t s_o0[K3A_DOCS_PER_CHUNK];
+  __shared__ int s_len[K3A_DOCS_PER_CHUNK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane % LPR, grp = lane / LPR;
   int32_t* wq = reinterpret_cast<int32_t*>(k3_smem + hb_words) + warp * K3_WQ;
@@ -382,109 +424,162 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
     k3_next_chunk(work, B, &s_b, &s_c);
     const int b = s_b;
     if (b < 0) break;
+    const int n = n_cand[b];
+    const int32_t* cb = cand + int64_t(b) * cand_cap;
+    if (tid < K3A_DOCS_PER_CHUNK) {  // stage the chunk's document extents
+      const int idx = s_c * K3A_DOCS_PER_CHUNK + tid;
+      int64_t o0 = 0;
+      int len = -1;  // -1: no such document
+      if (idx < n) {
+        const int d = cb[idx];
+        o0 = doc_offsets[d];
+        len = int(doc_offsets[d + 1] - o0);
+      }
+      s_o0[tid] = o0;
+      s_len[tid] = len;
+    }
     if (b != cur_b) {  // CTA-uniform; every warp is past the previous chunk (barrier in k3_next_chunk)
       const uint4* src = reinterpret_cast<const uint4*>(hibits + int64_t(b) * hb_words);
       for (int i = tid; i < hb_words / 4; i += K3_THREADS) reinterpret_cast<uint4*>(bm)[i] = src[i];
       cur_b = b;
-      __syncthreads();
     }
-    const int n = n_cand[b];
+    __syncthreads();
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP) + sub;
-    const int32_t* cb = cand + int64_t(b) * cand_cap;
     const uint4* tqp = reinterpret_cast<const uint4*>(tau + int64_t(b) * QP + sub * 8);
 
-    for (int i = 0; i < K3A_DOCS_PER_CHUNK / 8; ++i) {
-      const int idx = s_c * K3A_DOCS_PER_CHUNK + i * 8 + warp;
-      if (idx >= n) break;
-      const int d = cb[idx];
-      const int64_t o0 = doc_offsets[d];
-      const int len = int(doc_offsets[d + 1] - o0);
-      // frame aligned to an absolute multiple of 32 tokens: every window is one 128-byte line of codes
-      const int64_t w0 = o0 & ~int64_t(31);
-      const int lo = int(o0 - w0), hi = lo + len;
-      const int32_t* cw = codes + w0 + lane;
-      int head = 0, tail = 0;
-      __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
-      for (int f0 = 0; f0 < hi; f0 += 128) {
-        int c[4];
+    // ---- the warp's documents are slots warp*DPW .. warp*DPW + DPW - 1 of the chunk, walked group by group ----
+    int slot = warp * DPW;
+    const int slot_end = slot + DPW;
+    int len = s_len[slot];
+    if (len < 0) continue;  // warp-uniform: this warp has no document in the (last, partial) chunk
+    int lo, hi, f0 = 0;
+    const int32_t* cw;
+    {
+      const int64_t o0 = s_o0[slot];
+      const int64_t w0 = o0 & ~int64_t(31);  // frame aligned to an absolute multiple of 32 tokens: one 128-byte line per window
+      lo = int(o0 - w0);
+      hi = lo + len;
+      cw = codes + w0 + lane;
+    }
+    int c[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int f = f0 + u * 32 + lane;
-          c[u] = (f >= lo && f < hi) ? __ldg(cw + f0 + u * 32) : -1;
+    for (int u = 0; u < 4; ++u) {
+      const int f = u * 32 + lane;
+      c[u] = (f >= lo && f < hi) ? __ldg(cw + u * 32) : -1;
+    }
+    int head = 0, tail = 0;
+    __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
+
+    for (;;) {
+      // ---- the next group: same document or the next slot; its code loads go out now ----
+      int nslot = slot, nf0 = f0 + 128, nlen = len, nlo = lo, nhi = hi;
+      const int32_t* ncw = cw;
+      const bool last_of_doc = nf0 >= hi;
+      if (last_of_doc) {
+        nslot = slot + 1;
+        nf0 = 0;
+        nlen = nslot < slot_end ? s_len[nslot] : -1;
+        if (nlen >= 0) {
+          const int64_t o0 = s_o0[nslot];
+          const int64_t w0 = o0 & ~int64_t(31);
+          nlo = int(o0 - w0);
+          nhi = nlo + nlen;
+          ncw = codes + w0 + lane;
         }
+      }
+      int nx[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (f0 + u * 32 < hi) {  // warp-uniform
-            const bool bit = c[u] >= 0 && ((bm[c[u] >> 5] >> (c[u] & 31)) & 1u);
-            const unsigned mask = __ballot_sync(0xffffffffu, bit);
-            if (bit) wq[(tail + __popc(mask & lt_mask)) & (K3_WQ - 1)] = c[u];
-            tail += __popc(mask);
-            __syncwarp();
-            while (tail - head >= FLUSH) {
-              uint4 v[U];
+      for (int u = 0; u < 4; ++u) {
+        const int f = nf0 + u * 32 + lane;
+        nx[u] = (nlen >= 0 && f >= nlo && f < nhi) ? __ldg(ncw + nf0 + u * 32) : -1;
+      }
+      // ---- current group: test the bit of every token, queue the high codes, gather full batches ----
 #pragma unroll
-              for (int k = 0; k < U; ++k) {
-                const int code = wq[(head + k * TPI + grp) & (K3_WQ - 1)];
-                v[k] = __ldg(Sb + int64_t(code) * LPR);
-              }
+      for (int u = 0; u < 4; ++u) {
+        if (f0 + u * 32 < hi) {  // warp-uniform
+          const bool bit = c[u] >= 0 && ((bm[c[u] >> 5] >> (c[u] & 31)) & 1u);
+          const unsigned mask = __ballot_sync(0xffffffffu, bit);
+          if (bit) wq[(tail + __popc(mask & lt_mask)) & (K3_WQ - 1)] = c[u];
+          tail += __popc(mask);
+          __syncwarp();
+          while (tail - head >= FLUSH) {
+            uint4 v[U];
 #pragma unroll
-              for (int k = 0; k < U; ++k) {
-                m0 = __hmax2(m0, u32_as_half2(v[k].x));
-                m1 = __hmax2(m1, u32_as_half2(v[k].y));
-                m2 = __hmax2(m2, u32_as_half2(v[k].z));
-                m3 = __hmax2(m3, u32_as_half2(v[k].w));
-              }
-              head += FLUSH;
+            for (int k = 0; k < U; ++k) {
+              const int code = wq[(head + k * TPI + grp) & (K3_WQ - 1)];
+              v[k] = __ldg(Sb + int64_t(code) * LPR);
             }
-            __syncwarp();
-          }
-        }
-      }
-      {  // drain: fewer than FLUSH codes left
-        const int rem = tail - head;
-        uint4 v[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-          const int jj = k * TPI + grp;
-          v[k] = make_uint4(half2_as_u32(sentinel), half2_as_u32(sentinel), half2_as_u32(sentinel),
-                            half2_as_u32(sentinel));
-          if (jj < rem) {
-            const int code = wq[(head + jj) & (K3_WQ - 1)];
-            v[k] = __ldg(Sb + int64_t(code) * LPR);
+            for (int k = 0; k < U; ++k) {
+              m0 = __hmax2(m0, u32_as_half2(v[k].x));
+              m1 = __hmax2(m1, u32_as_half2(v[k].y));
+              m2 = __hmax2(m2, u32_as_half2(v[k].z));
+              m3 = __hmax2(m3, u32_as_half2(v[k].w));
+            }
+            head += FLUSH;
           }
+          __syncwarp();
         }
+      }
+      if (last_of_doc) {
+        {  // drain: fewer than FLUSH codes left
+          const int rem = tail - head;
+          uint4 v[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-          m0 = __hmax2(m0, u32_as_half2(v[k].x));
-          m1 = __hmax2(m1, u32_as_half2(v[k].y));
-          m2 = __hmax2(m2, u32_as_half2(v[k].z));
-          m3 = __hmax2(m3, u32_as_half2(v[k].w));
+          for (int k = 0; k < U; ++k) {
+            const int jj = k * TPI + grp;
+            v[k] = make_uint4(half2_as_u32(sentinel), half2_as_u32(sentinel), half2_as_u32(sentinel),
+                              half2_as_u32(sentinel));
+            if (jj < rem) {
+              const int code = wq[(head + jj) & (K3_WQ - 1)];
+              v[k] = __ldg(Sb + int64_t(code) * LPR);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < U; ++k) {
+            m0 = __hmax2(m0, u32_as_half2(v[k].x));
+            m1 = __hmax2(m1, u32_as_half2(v[k].y));
+            m2 = __hmax2(m2, u32_as_half2(v[k].z));
+            m3 = __hmax2(m3, u32_as_half2(v[k].w));
+          }
+          __syncwarp();  // the next document's pushes may reuse these slots
         }
-        __syncwarp();  // the next document's pushes may reuse these slots
+        rows += unsigned(tail);
+        toks += unsigned(len);
+        k3_reduce_groups<LPR>(m0, m1, m2, m3);
+        // lower bound: the maxima over the gathered rows; upper bound: unresolved columns raised to tau
+        const uint4 tq = __ldg(tqp);
+        const __half2 t0 = u32_as_half2(tq.x), t1 = u32_as_half2(tq.y), t2 = u32_as_half2(tq.z), t3 = u32_as_half2(tq.w);
+        const int col0 = sub * 8;
+        const float lb = k3_sum_columns<LPR>(m0, m1, m2, m3, col0, Q);
+        const float ub = k3_sum_columns<LPR>(__hmax2(m0, t0), __hmax2(m1, t1), __hmax2(m2, t2), __hmax2(m3, t3), col0, Q);
+        // a column is unresolved when its maximum over the gathered rows is below tau (padded columns: tau = +inf,
+        // but they are outside the sums and must not count)
+        const unsigned l0 = __hlt2_mask(m0, t0) & ((col0 + 0 < Q ? 0xffffu : 0u) | (col0 + 1 < Q ? 0xffff0000u : 0u));
+        const unsigned l1 = __hlt2_mask(m1, t1) & ((col0 + 2 < Q ? 0xffffu : 0u) | (col0 + 3 < Q ? 0xffff0000u : 0u));
+        const unsigned l2 = __hlt2_mask(m2, t2) & ((col0 + 4 < Q ? 0xffffu : 0u) | (col0 + 5 < Q ? 0xffff0000u : 0u));
+        const unsigned l3 = __hlt2_mask(m3, t3) & ((col0 + 6 < Q ? 0xffffu : 0u) | (col0 + 7 < Q ? 0xffff0000u : 0u));
+        const bool unres = __any_sync(0xffffffffu, (l0 | l1 | l2 | l3) != 0u);
+        if (lane == 0) {
+          const int64_t at = int64_t(b) * cand_cap + (s_c * K3A_DOCS_PER_CHUNK + slot);
+          float l = lb;
+          if (!unres) l = ub;                                       // resolved: ub is the exact score
+          else if (!(l < ub)) l = ub - fabsf(ub) * 1e-6f - 1e-30f;  // keep "unresolved" visible as lb < ub
+          ub_out[at] = ub;
+          lb_out[at] = l;
+        }
+        if (nlen < 0) break;  // no further document for this warp in the chunk
+        head = tail = 0;
+        m0 = m1 = m2 = m3 = sentinel;
       }
-      rows += unsigned(tail);
-      toks += unsigned(len);
-      k3_reduce_groups<LPR>(m0, m1, m2, m3);
-      // lower bound: the maxima over the gathered rows; upper bound: unresolved columns raised to tau
-      const uint4 tq = __ldg(tqp);
-      const __half2 t0 = u32_as_half2(tq.x), t1 = u32_as_half2(tq.y), t2 = u32_as_half2(tq.z), t3 = u32_as_half2(tq.w);
-      const int col0 = sub * 8;
-      const float lb = k3_sum_columns<LPR>(m0, m1, m2, m3, col0, Q);
-      const float ub = k3_sum_columns<LPR>(__hmax2(m0, t0), __hmax2(m1, t1), __hmax2(m2, t2), __hmax2(m3, t3), col0, Q);
-      // a column is unresolved when its maximum over the gathered rows is below tau (padded columns: tau = +inf,
-      // but they are outside the sums and must not count)
-      const unsigned lt = __hlt2_mask(m0, t0) & ((col0 + 0 < Q ? 0xffffu : 0u) | (col0 + 1 < Q ? 0xffff0000u : 0u));
-      const unsigned lt1 = __hlt2_mask(m1, t1) & ((col0 + 2 < Q ? 0xffffu : 0u) | (col0 + 3 < Q ? 0xffff0000u : 0u));
-      const unsigned lt2 = __hlt2_mask(m2, t2) & ((col0 + 4 < Q ? 0xffffu : 0u) | (col0 + 5 < Q ? 0xffff0000u : 0u));
-      const unsigned lt3 = __hlt2_mask(m3, t3) & ((col0 + 6 < Q ? 0xffffu : 0u) | (col0 + 7 < Q ? 0xffff0000u : 0u));
-      const bool unres = __any_sync(0xffffffffu, (lt | lt1 | lt2 | lt3) != 0u);
-      if (lane == 0) {
-        float l = lb;
-        if (!unres) l = ub;                                            // resolved: ub is the exact score
-        else if (!(l < ub)) l = ub - fabsf(ub) * 1e-6f - 1e-30f;       // keep "unresolved" visible as lb < ub
-        ub_out[int64_t(b) * cand_cap + idx] = ub;
-        lb_out[int64_t(b) * cand_cap + idx] = l;
-      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c[u] = nx[u];
+      slot = nslot;
+      f0 = nf0;
+      len = nlen;
+      lo = nlo;
+      hi = nhi;
+      cw = ncw;
     }
   }
   if (stats && lane == 0) {
@@ -965,15 +1060,15 @@ int launch_k3_exact(const fpb_index* ix, const Ws& ws, const int32_t* list, cons
   return FPB_OK;
 }
 
-// the quantile of the tile maxima that defines a "high" score; FPB_K3_TAU_Q overrides it (tuning only: every
-// value gives the same results)
-float k3_tau_quantile() {
-  static const float q = [] {
-    const char* e = getenv("FPB_K3_TAU_Q");
-    const float v = e ? float(atof(e)) : 0.5f;
-    return v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+// LAMBDA of k3_tau_kernel: the expected number of tokens per candidate and column at or above tau.  FPB_K3_LAMBDA
+// overrides it (tuning only: every value gives the same results).
+float k3_tau_lambda() {
+  static const float v = [] {
+    const char* e = getenv("FPB_K3_LAMBDA");
+    const float x = e ? float(atof(e)) : 1.6f;
+    return x < 0.01f ? 0.01f : (x > 64.f ? 64.f : x);
   }();
-  return q;
+  return v;
 }
 
 template <int LPR>
@@ -986,7 +1081,8 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
     FPB_LAUNCH_CHECK("k3_prefix");
     return launch_k3_exact<LPR>(ix, ws, nullptr, nullptr, ws.work(), st);
   }
-  k3_tau_kernel<<<L.B * L.Qp, 256, 0, st>>>(ws.tmax(), L.n_tiles, L.Q, L.Qp, k3_tau_quantile(), ws.tau());
+  k3_tau_kernel<LPR><<<L.B, K3_TAU_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes, ws.cand(),
+                                                     L.cand_cap, ws.n_cand(), k3_tau_lambda(), ws.tau());
   FPB_LAUNCH_CHECK("k3_tau");
   {
     dim3 grid(unsigned((ix->K + 255) / 256), unsigned(L.B));
@@ -997,8 +1093,8 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
   FPB_LAUNCH_CHECK("k3_prefix");
   {
     // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)
-    static const int minb = getenv("FPB_K3_MINB") ? atoi(getenv("FPB_K3_MINB")) : 6;  // tuning: 5 (48 regs) or 6 (40)
-    auto kern = minb == 5 ? k3_bound_kernel<LPR, 5> : k3_bound_kernel<LPR, 6>;
+    static const int minb = getenv("FPB_K3_MINB") ? atoi(getenv("FPB_K3_MINB")) : 5;  // tuning: CTAs per SM (4: 64 registers, 5: 48, 6: 40)
+    auto kern = minb == 4 ? k3_bound_kernel<LPR, 4> : (minb == 6 ? k3_bound_kernel<LPR, 6> : k3_bound_kernel<LPR, 5>);
     FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = int((227 * 1024) / (smem + 1024 + 64));
     per_sm = per_sm < 1 ? 1 : (per_sm > minb ? minb : per_sm);

@@ -29,11 +29,21 @@ to a few per cent, which moves the time from the approximate stage to the fixed-
 from __future__ import annotations
 
 import math
+import os
+import types
 
 import torch
 
-from ..engine import IndexTensors
-from . import build
+if __package__:
+    from .layout import build_ivf, num_partitions_for
+else:  # loaded by file path (bench.py --impl reference): keep the package and its shared libraries out
+    import importlib.util
+
+    _spec = importlib.util.spec_from_file_location(
+        "_fpb_layout", os.path.join(os.path.dirname(os.path.abspath(__file__)), "layout.py"))
+    _layout = importlib.util.module_from_spec(_spec)
+    _spec.loader.exec_module(_layout)
+    build_ivf, num_partitions_for = _layout.build_ivf, _layout.num_partitions_for
 
 
 def _normal_quantiles(n: int, sigma: float) -> torch.Tensor:
@@ -42,12 +52,13 @@ def _normal_quantiles(n: int, sigma: float) -> torch.Tensor:
 
 
 @torch.inference_mode()
-def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, device: str = "cuda:0",
-                    seed: int = 1234, doc_range: tuple[int, int] | None = None, ragged: bool = False,
-                    sigma: float = 0.05, docs_per_chunk: int = 25_000, topics: int = 0,
-                    mix: float = 0.05) -> tuple[IndexTensors, int]:
-    """Returns (tensors on `device`, doc_id_base).  `doc_range=(lo, hi)` generates only that
-    slice of the global index (document sharding); ids in the IVF are then local."""
+def synthetic_arrays(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, device: str = "cuda:0",
+                     seed: int = 1234, doc_range: tuple[int, int] | None = None, ragged: bool = False,
+                     sigma: float = 0.05, docs_per_chunk: int = 25_000, topics: int = 0,
+                     mix: float = 0.05) -> tuple[types.SimpleNamespace, int]:
+    """Returns (arrays on `device` with the field names of engine.IndexTensors, doc_id_base), using torch only.
+    `doc_range=(lo, hi)` generates only that slice of the global index (document sharding); ids in the IVF are
+    then local."""
     dev = torch.device(device)
     lo, hi = (0, n_docs) if doc_range is None else doc_range
     g = torch.Generator(device=dev)
@@ -59,7 +70,7 @@ def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, d
     else:
         lengths = torch.full((n_docs,), doc_len, dtype=torch.int64)
     total_tokens = int(lengths.sum())
-    K = build.num_partitions_for(float(total_tokens))
+    K = num_partitions_for(float(total_tokens))
     centroids = torch.randn(K, dim, generator=g, device=dev)
     block = 0
     if topics > 0:
@@ -104,8 +115,8 @@ def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, d
         codes[d0 : d0 + (s1 - s0)] = cc[s0:s1]
         residuals[d0 : d0 + (s1 - s0)] = rr[s0:s1]
         del cc, rr
-    ivf, ivf_lengths = build.build_ivf(codes[:n_tok], my_lengths, K)
-    data = IndexTensors(
+    ivf, ivf_lengths = build_ivf(codes[:n_tok], my_lengths, K)
+    data = types.SimpleNamespace(
         nbits=nbits,
         centroids=centroids,
         bucket_weights=weights,
@@ -116,3 +127,13 @@ def synthetic_index(n_docs: int, doc_len: int, dim: int = 128, nbits: int = 4, d
         ivf_lengths=ivf_lengths,
     )
     return data, lo
+
+
+def synthetic_index(*args, **kwargs):
+    """`synthetic_arrays` as engine.IndexTensors (what DeviceIndex takes)."""
+    from ..engine import IndexTensors
+
+    a, base = synthetic_arrays(*args, **kwargs)
+    return IndexTensors(nbits=a.nbits, centroids=a.centroids, bucket_weights=a.bucket_weights,
+                        doc_lengths=a.doc_lengths, doc_codes=a.doc_codes, doc_residuals=a.doc_residuals,
+                        ivf=a.ivf, ivf_lengths=a.ivf_lengths), base

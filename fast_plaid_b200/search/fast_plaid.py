@@ -579,6 +579,33 @@ class FastPlaid:
         """Bench / test helper: put already-built index tensors straight into HBM."""
         return DeviceIndex(data, device, doc_id_base=doc_id_base)
 
+    @classmethod
+    def from_device_index(cls, didx: DeviceIndex, index_dir: str | None = None,
+                          shard: tuple[int, int] | None = None) -> "FastPlaid":
+        """A FastPlaid whose index is ALREADY resident in HBM (bench / serving processes that build or receive
+        the tensors in memory): `search` runs the same code as for a directory-backed index -- reload check,
+        query preparation, C-ABI call, result lists -- the directory only holds the `metadata.json` that check
+        looks at."""
+        import tempfile
+
+        self = cls.__new__(cls)
+        self.devices = [str(didx.device)]
+        self.index = index_dir or tempfile.mkdtemp(prefix="fpb_attached_")
+        os.makedirs(self.index, exist_ok=True)
+        self.low_memory = False
+        self.shard = shard
+        meta_path = os.path.join(self.index, "metadata.json")
+        if not os.path.exists(meta_path):
+            with open(meta_path, "w") as f:
+                json.dump({"num_documents": didx.num_documents, "nbits": didx.nbits, "attached": True}, f)
+        self.lock_path = os.path.join(self.index, "plaid.lock")
+        self.lock = FileLock(self.lock_path) if FileLock is not None else _NullLock()
+        self._index_swap_lock = threading.Lock()
+        self.indices = {self.devices[0]: didx}
+        self._cpu_loaded = True
+        self._last_known_mtime = Path(meta_path).stat().st_mtime
+        return self
+
 
 def read_num_documents(index_path: str) -> int:
     with open(os.path.join(index_path, "metadata.json")) as f:

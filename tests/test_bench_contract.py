@@ -43,3 +43,52 @@ def test_bench_configs_cover_the_baseline_configs():
     assert {"cfg2", "cfg3", "cfg4", "cfg5"} <= set(bench.CONFIGS)
     assert bench.CONFIGS["cfg3"]["n_docs"] == 1_000_000 and bench.CONFIGS["cfg3"]["top_k"] == 100
     assert "north_star" in base
+
+
+def test_parity_sample_classifier_on_an_oracle_stand_in():
+    """bench.parity_sample, fed the oracle's own results in place of the engine's: nothing to explain, every list
+    identical; and with one returned document swapped for a far-away one it must report the mismatch."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    from util import build_oracle_index, make_docs, make_queries
+
+    from oracle import plaid_oracle as po
+
+    docs = make_docs(300, 10, 40, seed=3)
+    oidx, _ = build_oracle_index(docs, kmeans_niters=2)
+    queries = make_queries(4, 16, seed=5, docs=docs)
+
+    class P:
+        n_ivf_probe, n_full_scores, top_k = 4, 64, 5
+
+    S, results, stages = [], [], []
+    for b in range(4):
+        st = po.search_one(queries[b], oidx, 4, 2000, 64, 5, ties="canonical", return_stages=True)
+        S.append(st["S"])
+        results.append(list(zip(st["ids"], st["scores"])))
+        stages.append(st)
+    gpu = {"S": torch.stack(S), "results": results}
+    out = bench.parity_sample(po, oidx, queries, P, gpu, world=2)
+    assert out["queries"] == 4 and out["identical_id_lists"] == 4 and out["identical_id_lists_given_gpu_S"] == 4
+    assert out["unexplained_mismatches"] == 0 and out["S_max_fp16_ulp"] == 0
+    # single-GPU form: the integer stages are compared too
+    R = max(len(s["rerank"]) for s in stages)
+    C = max(len(s["candidates"]) for s in stages)
+    cells = torch.full((4, 16, 4), -1, dtype=torch.int32)
+    cand = torch.zeros((4, C), dtype=torch.int32)
+    rer = torch.zeros((4, R), dtype=torch.int32)
+    for b, s in enumerate(stages):
+        cells[b].view(-1)[: s["probe_cells"].numel()] = s["probe_cells"].to(torch.int32)
+        cand[b, : len(s["candidates"])] = s["candidates"].to(torch.int32)
+        rer[b, : len(s["rerank"])] = s["rerank"].to(torch.int32)
+    gpu1 = dict(gpu, cells=cells, cand=cand, rerank=rer,
+                n_cand=torch.tensor([len(s["candidates"]) for s in stages]),
+                n_rerank=torch.tensor([len(s["rerank"]) for s in stages]))
+    assert bench.parity_sample(po, oidx, queries, P, gpu1, world=1)["unexplained_mismatches"] == 0
+    # a wrong document in the result must not pass
+    bad = [list(r) for r in results]
+    worst = int(stages[0]["rerank"][stages[0]["exact"].argmin()])
+    if worst != bad[0][0][0]:
+        bad[0][0] = (worst, bad[0][0][1])
+        out = bench.parity_sample(po, oidx, queries, P, dict(gpu, results=bad), world=2)
+        assert out["unexplained_mismatches"] > 0

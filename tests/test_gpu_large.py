@@ -83,7 +83,7 @@ def test_sample_against_oracle(big, cuda_device):
         assert torch.equal(d_rerank[b], st["rerank"][b]) and torch.equal(d_ids[b], st["ids"][b])
         assert torch.equal(d_scores[b], st["scores"][b])
         assert bool((d_ub[b, :n] >= st["approx"][b, :n]).all())
-        assert int(d_nref[b]) < n // 4, f"query {b}: the exact pass re-scored {int(d_nref[b])} of {n} candidates"
+        assert int(d_nref[b]) < n // 2, f"query {b}: the exact pass re-scored {int(d_nref[b])} of {n} candidates"
     for b in range(3):
         # integer stages bit-exact given the GPU's S (canonical ties), at 50k+ candidates per query
         S_b = st["S"][b, :, :Q].cpu().contiguous()
