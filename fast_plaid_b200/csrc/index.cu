@@ -47,7 +47,7 @@ void fpb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* fpb_last_error(void) { return g_err; }
-extern "C" int fpb_abi_version(void) { return 4; }  // 4: two-pass approximate stage (layout fields, FPB_FLAG_APPROX_*)
+extern "C" int fpb_abi_version(void) { return 5; }  // 5: two-pass approximate stage (layout fields, FPB_FLAG_APPROX_*), fpb_comm_* + fpb_search_batch_sharded
 
 static int bitrev(int x, int nbits) {
   int r = 0;

@@ -32,7 +32,8 @@ namespace {
 constexpr int K3_THREADS = 256;
 constexpr int K3_DOCS_PER_CHUNK = 64;    // exact pass: work-queue granule
 constexpr int K3A_DOCS_PER_CHUNK = 128;  // bound pass
-constexpr int K3_WQ = 128;               // bound pass: per-warp ring of high codes waiting for their gather
+// bound pass: per-warp ring of high codes waiting for their gather (a power of two >= one group + one batch)
+constexpr int K3_WQ_FOR(int W, int FLUSH) { int n = 64; while (n < 32 * W + FLUSH) n <<= 1; return n; }
 
 // chunk prefix of the dynamic work queue: work[b] = first chunk of query b, work[B] = total, work[B+1] = counter
 __global__ void k3_prefix_kernel(const int32_t* __restrict__ n_items, int B, int per_chunk,
@@ -393,7 +394,7 @@ k3_hibits_kernel(const __half* __restrict__ S, int64_t K, const __half* __restri
 // candidate -> offset loads are paid once per chunk, not once per document).  A warp walks its documents as a stream
 // of 128-token groups and always has the NEXT group's code loads in flight while it tests, queues and gathers the
 // current one: the pass is otherwise a chain of dependent latencies (codes from HBM, then the gathers from L2).
-template <int LPR, int MINB>
+template <int LPR, int MINB, int W, int U>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
                 const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
@@ -402,10 +403,10 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
                 float* __restrict__ ub_out, float* __restrict__ lb_out, unsigned long long* __restrict__ stats) {
   constexpr int QP = LPR * 8;
   constexpr int TPI = 32 / LPR;          // rows per warp-wide gather
-  constexpr int U = (LPR <= 4) ? 4 : 8;  // gathers in flight per lane
   constexpr int FLUSH = U * TPI;         // rows per flush (<= 64)
   constexpr int DPW = K3A_DOCS_PER_CHUNK / (K3_THREADS / 32);  // documents per warp and chunk
-  static_assert(FLUSH + 32 <= K3_WQ, "ring too small");
+  constexpr int WQ = K3_WQ_FOR(W, FLUSH);  // ring entries per warp: one group of pushes on top of an unflushed rest
+  static_assert(FLUSH + 32 * W <= WQ, "ring too small");
   extern __shared__ __align__(16) uint32_t k3_smem[];
   uint32_t* bm = k3_smem;
   __shared__ int s_b, s_c;
@@ -413,7 +414,7 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
   __shared__ int s_len[K3A_DOCS_PER_CHUNK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane % LPR, grp = lane / LPR;
-  int32_t* wq = reinterpret_cast<int32_t*>(k3_smem + hb_words) + warp * K3_WQ;
+  int32_t* wq = reinterpret_cast<int32_t*>(k3_smem + hb_words) + warp * WQ;
   unsigned lt_mask;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
   const __half2 sentinel = __float2half2_rn(FPB_PAD_SENTINEL);
@@ -461,9 +462,9 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
       hi = lo + len;
       cw = codes + w0 + lane;
     }
-    int c[4];
+    int c[W];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < W; ++u) {
       const int f = u * 32 + lane;
       c[u] = (f >= lo && f < hi) ? __ldg(cw + u * 32) : -1;
     }
@@ -472,7 +473,7 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
 
     for (;;) {
       // ---- the next group: same document or the next slot; its code loads go out now ----
-      int nslot = slot, nf0 = f0 + 128, nlen = len, nlo = lo, nhi = hi;
+      int nslot = slot, nf0 = f0 + 32 * W, nlen = len, nlo = lo, nhi = hi;
       const int32_t* ncw = cw;
       const bool last_of_doc = nf0 >= hi;
       if (last_of_doc) {
@@ -487,40 +488,43 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
           ncw = codes + w0 + lane;
         }
       }
-      int nx[4];
+      int nx[W];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < W; ++u) {
         const int f = nf0 + u * 32 + lane;
         nx[u] = (nlen >= 0 && f >= nlo && f < nhi) ? __ldg(ncw + nf0 + u * 32) : -1;
       }
-      // ---- current group: test the bit of every token, queue the high codes, gather full batches ----
+      // ---- current group: test the bit of every token (independent shared-memory reads), queue the high codes,
+      //      then gather in full batches ----
+      bool bit[W];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < W; ++u) bit[u] = c[u] >= 0 && ((bm[c[u] >> 5] >> (c[u] & 31)) & 1u);
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
         if (f0 + u * 32 < hi) {  // warp-uniform
-          const bool bit = c[u] >= 0 && ((bm[c[u] >> 5] >> (c[u] & 31)) & 1u);
-          const unsigned mask = __ballot_sync(0xffffffffu, bit);
-          if (bit) wq[(tail + __popc(mask & lt_mask)) & (K3_WQ - 1)] = c[u];
+          const unsigned mask = __ballot_sync(0xffffffffu, bit[u]);
+          if (bit[u]) wq[(tail + __popc(mask & lt_mask)) & (WQ - 1)] = c[u];
           tail += __popc(mask);
-          __syncwarp();
-          while (tail - head >= FLUSH) {
-            uint4 v[U];
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-              const int code = wq[(head + k * TPI + grp) & (K3_WQ - 1)];
-              v[k] = __ldg(Sb + int64_t(code) * LPR);
-            }
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-              m0 = __hmax2(m0, u32_as_half2(v[k].x));
-              m1 = __hmax2(m1, u32_as_half2(v[k].y));
-              m2 = __hmax2(m2, u32_as_half2(v[k].z));
-              m3 = __hmax2(m3, u32_as_half2(v[k].w));
-            }
-            head += FLUSH;
-          }
-          __syncwarp();
         }
       }
+      __syncwarp();
+      while (tail - head >= FLUSH) {
+        uint4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int code = wq[(head + k * TPI + grp) & (WQ - 1)];
+          v[k] = __ldg(Sb + int64_t(code) * LPR);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          m0 = __hmax2(m0, u32_as_half2(v[k].x));
+          m1 = __hmax2(m1, u32_as_half2(v[k].y));
+          m2 = __hmax2(m2, u32_as_half2(v[k].z));
+          m3 = __hmax2(m3, u32_as_half2(v[k].w));
+        }
+        head += FLUSH;
+      }
+      __syncwarp();
       if (last_of_doc) {
         {  // drain: fewer than FLUSH codes left
           const int rem = tail - head;
@@ -531,7 +535,7 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
             v[k] = make_uint4(half2_as_u32(sentinel), half2_as_u32(sentinel), half2_as_u32(sentinel),
                               half2_as_u32(sentinel));
             if (jj < rem) {
-              const int code = wq[(head + jj) & (K3_WQ - 1)];
+              const int code = wq[(head + jj) & (WQ - 1)];
               v[k] = __ldg(Sb + int64_t(code) * LPR);
             }
           }
@@ -573,7 +577,7 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
         m0 = m1 = m2 = m3 = sentinel;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) c[u] = nx[u];
+      for (int u = 0; u < W; ++u) c[u] = nx[u];
       slot = nslot;
       f0 = nf0;
       len = nlen;
@@ -1074,9 +1078,8 @@ float k3_tau_lambda() {
 template <int LPR>
 int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
-  const size_t smem = size_t(L.hb_words) * 4 + size_t(K3_THREADS / 32) * K3_WQ * 4;
   // one-pass scoring: asked for, or the K-bit map of a query does not fit next to a second CTA's
-  if ((flags & FPB_FLAG_APPROX_DIRECT) || smem > 100 * 1024) {
+  if ((flags & FPB_FLAG_APPROX_DIRECT) || size_t(L.hb_words) * 4 > 96 * 1024) {
     k3_prefix_kernel<<<1, 32, 0, st>>>(ws.n_cand(), L.B, K3_DOCS_PER_CHUNK, ws.work());
     FPB_LAUNCH_CHECK("k3_prefix");
     return launch_k3_exact<LPR>(ix, ws, nullptr, nullptr, ws.work(), st);
@@ -1093,10 +1096,23 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
   FPB_LAUNCH_CHECK("k3_prefix");
   {
     // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)
-    static const int minb = getenv("FPB_K3_MINB") ? atoi(getenv("FPB_K3_MINB")) : 5;  // tuning: CTAs per SM (4: 64 registers, 5: 48, 6: 40)
-    auto kern = minb == 4 ? k3_bound_kernel<LPR, 4> : (minb == 6 ? k3_bound_kernel<LPR, 6> : k3_bound_kernel<LPR, 5>);
+    // shape of the walk: W 32-token windows per group (all their code loads in flight at once, the next group's
+    // prefetched), U gathers per lane and batch.  FPB_K3_SHAPE picks one of the compiled shapes (tuning).
+    static const int shape = getenv("FPB_K3_SHAPE") ? atoi(getenv("FPB_K3_SHAPE")) : 0;
+    void (*kern)(const __half*, int64_t, int, const int64_t*, const int32_t*, const int32_t*, int, const int32_t*,
+                 int32_t*, int, const __half*, const uint32_t*, int, float*, float*, unsigned long long*);
+    int minb, wq;
+    constexpr int TPI = 32 / LPR;
+    switch (shape) {
+      case 1: kern = k3_bound_kernel<LPR, 5, 4, 4>; minb = 5; wq = K3_WQ_FOR(4, 4 * TPI); break;
+      case 2: kern = k3_bound_kernel<LPR, 3, 12, 8>; minb = 3; wq = K3_WQ_FOR(12, 8 * TPI); break;
+      case 3: kern = k3_bound_kernel<LPR, 4, 6, 8>; minb = 4; wq = K3_WQ_FOR(6, 8 * TPI); break;
+      default: kern = k3_bound_kernel<LPR, 4, 12, 4>; minb = 4; wq = K3_WQ_FOR(12, 4 * TPI); break;
+    }
+    const size_t smem = size_t(L.hb_words) * 4 + size_t(K3_THREADS / 32) * wq * 4;
     FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int per_sm = int((227 * 1024) / (smem + 1024 + 64));
+    // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)
+    int per_sm = int((227 * 1024) / (smem + 1024 + 2048));
     per_sm = per_sm < 1 ? 1 : (per_sm > minb ? minb : per_sm);
     kern<<<ix->sm_count * per_sm, K3_THREADS, smem, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes, ws.cand(),
                                                           L.cand_cap, ws.n_cand(), ws.work(), L.B, ws.tau(),

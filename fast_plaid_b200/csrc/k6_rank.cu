@@ -263,8 +263,10 @@ int launch_emit_keys(const fpb_index* ix, const Ws& ws, uint64_t* d_keys, cudaSt
   return FPB_OK;
 }
 
-int launch_apply_threshold(const Ws& ws, const uint64_t* d_all_keys, int n_shards, int rank, cudaStream_t st) {
+int launch_apply_threshold(const Ws& ws, const uint64_t* d_all_keys, int n_shards, int rank, cudaStream_t st,
+                           int b_stride) {
   const fpb_layout& L = *ws.L;
+  if (b_stride <= 0) b_stride = L.B;  // queries per shard in the gathered key array
   const int P = fpb_next_pow2(n_shards * L.R);
   const size_t smem = size_t(P) * 8;
   if (smem > 200 * 1024) {
@@ -273,7 +275,7 @@ int launch_apply_threshold(const Ws& ws, const uint64_t* d_all_keys, int n_shard
   }
   // opt in on every launch: the attribute is per device and the call costs about a microsecond
   FPB_CUDA_CHECK(cudaFuncSetAttribute(apply_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  apply_threshold_kernel<<<L.B, 1024, smem, st>>>(d_all_keys, n_shards, rank, L.B, L.R, P, ws.n_rerank(),
+  apply_threshold_kernel<<<L.B, 1024, smem, st>>>(d_all_keys, n_shards, rank, b_stride, L.R, P, ws.n_rerank(),
                                                   ws.rerank(), ws.rerank_approx());
   FPB_LAUNCH_CHECK("apply_threshold");
   return FPB_OK;
@@ -300,10 +302,19 @@ int launch_emit_records(const fpb_index* ix, const Ws& ws, fpb_record* d_records
 
 extern "C" int fpb_merge_shards(const fpb_record* d_all_records, int n_shards, int B, int R, int top_k,
                                 int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, void* stream) {
-  if (!d_all_records || n_shards < 1 || B < 1 || R < 1 || top_k < 1) {
+  return launch_merge(d_all_records, n_shards, B, B, R, top_k, d_out_ids, d_out_scores, d_out_counts,
+                      static_cast<cudaStream_t>(stream));
+}
+
+// merge of the first `n_queries` queries of gathered records laid out [n_shards, b_stride, R]
+int launch_merge(const fpb_record* d_all_records, int n_shards, int b_stride, int n_queries, int R, int top_k,
+                 int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, cudaStream_t stream) {
+  const int B = b_stride;
+  if (!d_all_records || n_shards < 1 || B < 1 || R < 1 || top_k < 1 || n_queries < 0 || n_queries > B) {
     fpb_set_error("fpb_merge_shards: bad arguments");
     return FPB_ERR_INVALID;
   }
+  if (n_queries == 0) return FPB_OK;
   const int P = fpb_next_pow2(n_shards * R);
   const int Rp2 = fpb_next_pow2(R);
   const size_t smem = size_t(P + Rp2) * 8 + size_t(P) * 4;
@@ -313,8 +324,8 @@ extern "C" int fpb_merge_shards(const fpb_record* d_all_records, int n_shards, i
   }
   // opt in on every launch: the attribute is per device and the call costs about a microsecond
   FPB_CUDA_CHECK(cudaFuncSetAttribute(k6_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  k6_merge_kernel<<<B, 1024, smem, static_cast<cudaStream_t>(stream)>>>(d_all_records, n_shards, B, R, P, Rp2,
-                                                                       top_k, d_out_ids, d_out_scores, d_out_counts);
+  k6_merge_kernel<<<n_queries, 1024, smem, stream>>>(d_all_records, n_shards, B, R, P, Rp2, top_k, d_out_ids,
+                                                    d_out_scores, d_out_counts);
   FPB_LAUNCH_CHECK("k6_merge");
   return FPB_OK;
 }

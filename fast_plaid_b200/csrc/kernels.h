@@ -54,5 +54,8 @@ int launch_maxsim_v5(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* h
 int launch_rank(const fpb_index* ix, const Ws& ws, int top_k, int64_t* d_out_ids, float* d_out_scores,
                 int32_t* d_out_counts, cudaStream_t st);                          // K6
 int launch_emit_keys(const fpb_index* ix, const Ws& ws, uint64_t* d_keys, cudaStream_t st);
-int launch_apply_threshold(const Ws& ws, const uint64_t* d_all_keys, int n_shards, int rank, cudaStream_t st);
+int launch_apply_threshold(const Ws& ws, const uint64_t* d_all_keys, int n_shards, int rank, cudaStream_t st,
+                           int b_stride = 0);
+int launch_merge(const fpb_record* d_all_records, int n_shards, int b_stride, int n_queries, int R, int top_k,
+                 int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, cudaStream_t stream);
 int launch_emit_records(const fpb_index* ix, const Ws& ws, fpb_record* d_records, cudaStream_t st);

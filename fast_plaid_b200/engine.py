@@ -120,6 +120,13 @@ EXPORTED_SYMBOLS = [
     "fpb_shard_subset_keys",
     "fpb_shard_apply_threshold",
     "fpb_shard_exact_records",
+    "fpb_comm_unique_id",
+    "fpb_comm_create",
+    "fpb_comm_destroy",
+    "fpb_comm_nccl_version",
+    "fpb_sharded_scratch_bytes",
+    "fpb_search_batch_sharded",
+    "fpb_search_batch_sharded_host",
     "fpb_reconstruct",
     "fpb_token_scores",
     "fpb_encode",
@@ -192,6 +199,21 @@ def load_library() -> ctypes.CDLL:
         lib.fpb_shard_apply_threshold.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp]
         lib.fpb_shard_exact_records.restype = i32
         lib.fpb_shard_exact_records.argtypes = [vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, vp]
+        lib.fpb_comm_unique_id.restype = i32
+        lib.fpb_comm_unique_id.argtypes = [vp]
+        lib.fpb_comm_create.restype = i32
+        lib.fpb_comm_create.argtypes = [ctypes.POINTER(vp), i32, i32, vp, i32]
+        lib.fpb_comm_destroy.restype = None
+        lib.fpb_comm_destroy.argtypes = [vp]
+        lib.fpb_comm_nccl_version.restype = i32
+        lib.fpb_sharded_scratch_bytes.restype = i64
+        lib.fpb_sharded_scratch_bytes.argtypes = [i32, i32, i32]
+        lib.fpb_search_batch_sharded.restype = i32
+        lib.fpb_search_batch_sharded.argtypes = [vp, vp, i32, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp, sz,
+                                                 vp, vp, vp, vp]
+        lib.fpb_search_batch_sharded_host.restype = i32
+        lib.fpb_search_batch_sharded_host.argtypes = [vp, vp, i32, vp, i32, i32, ctypes.POINTER(FpbParams), vp, sz, vp,
+                                                      sz, vp, vp, vp, vp, vp, vp, vp, vp]
         lib.fpb_merge_shards.restype = i32
         lib.fpb_merge_shards.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp]
         lib.fpb_reconstruct.restype = i32
@@ -349,6 +371,65 @@ def upload_narrow(src: torch.Tensor, device: torch.device, dtype: torch.dtype) -
             done[slot].record(copy_stream)
     copy_stream.synchronize()
     return out
+
+
+FPB_COMM_ID_BYTES = 128
+
+
+class ShardComm:
+    """One NCCL communicator created below the C ABI (fpb_comm_*), used by the document-sharded search.
+
+    `ShardComm.from_process_group(device)` bootstraps it from an initialised torch.distributed group: rank 0
+    makes the id, the 128 bytes travel through the group's own broadcast (any backend), every rank joins.
+    `n_query_groups` x (world / n_query_groups) document shards is the search grid (csrc/comm.cu)."""
+
+    def __init__(self, nranks: int, rank: int, unique_id: bytes, device: torch.device | str) -> None:
+        _require_cuda()
+        self._lib = load_library()
+        self.device = torch.device(device)
+        self.nranks, self.rank = int(nranks), int(rank)
+        if len(unique_id) != FPB_COMM_ID_BYTES:
+            raise ValueError("unique_id must be FPB_COMM_ID_BYTES bytes")
+        buf = ctypes.create_string_buffer(bytes(unique_id), FPB_COMM_ID_BYTES)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(self._lib.fpb_comm_create(ctypes.byref(handle), self.nranks, self.rank, buf, self.device.index))
+        self._handle = handle
+
+    @staticmethod
+    def new_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(FPB_COMM_ID_BYTES)
+        _check(load_library().fpb_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_process_group(cls, device: torch.device | str) -> "ShardComm":
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.new_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(world, rank, box[0], device)
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.fpb_comm_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def shard_grid(rank: int, world: int, n_query_groups: int) -> tuple[int, int, int]:
+    """(query group, document shard, document shards per group) of `rank` on the n_query_groups x n_shards grid
+    of csrc/comm.cu."""
+    if n_query_groups < 1 or world % n_query_groups != 0:
+        raise ValueError(f"{n_query_groups} query groups do not divide {world} ranks")
+    n_shards = world // n_query_groups
+    return rank // n_shards, rank % n_shards, n_shards
 
 
 class DeviceIndex:
@@ -662,6 +743,50 @@ class DeviceIndex:
                 )
             )
         return rec
+
+    # the whole sharded search in one C-ABI call (both NCCL all-gathers issued inside, csrc/comm.cu)
+    def _sharded_io(self, comm: ShardComm, n_query_groups: int, B: int, Q: int, params: FpbParams):
+        b_local = -(-B // n_query_groups)
+        buf, lay = self.workspace(b_local, Q, params)
+        need = int(self._lib.fpb_sharded_scratch_bytes(b_local, lay.R, comm.nranks))
+        if getattr(self, "_scratch", None) is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return buf, self._scratch
+
+    def search_sharded(self, comm: ShardComm, n_query_groups: int, queries: torch.Tensor,
+                       params: FpbParams) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """queries: fp16 [B, Q, D] on this device, the SAME batch on every rank of `comm` (collective call).
+        Returns device tensors (ids, scores, counts) for all B queries."""
+        queries = queries.contiguous()
+        B, Q, _ = queries.shape
+        k = params.top_k
+        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        scores = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        with self._exclusive(), torch.cuda.device(self.device):
+            buf, scratch = self._sharded_io(comm, n_query_groups, B, Q, params)
+            _check(self._lib.fpb_search_batch_sharded(
+                self._handle, comm._handle, n_query_groups, queries.data_ptr(), B, Q, ctypes.byref(params),
+                buf.data_ptr(), buf.numel(), scratch.data_ptr(), scratch.numel(), ids.data_ptr(), scores.data_ptr(),
+                counts.data_ptr(), self._stream()))
+        return ids, scores, counts
+
+    def search_sharded_host(self, comm: ShardComm, n_query_groups: int, queries_host: torch.Tensor,
+                            params: FpbParams) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Host-buffer form of `search_sharded`: fp32/fp16 queries in HOST memory in, host tensors out."""
+        B, Q, D = queries_host.shape
+        if D != self.dim:
+            raise ValueError(f"query dim {D} != index dim {self.dim}")
+        with self._exclusive(), torch.cuda.device(self.device):
+            io = self._host_io(B, Q, params.top_k)
+            self._cast_into_pinned(queries_host, io["h_q"])
+            buf, scratch = self._sharded_io(comm, n_query_groups, B, Q, params)
+            _check(self._lib.fpb_search_batch_sharded_host(
+                self._handle, comm._handle, n_query_groups, io["h_q"].data_ptr(), B, Q, ctypes.byref(params),
+                buf.data_ptr(), buf.numel(), scratch.data_ptr(), scratch.numel(), io["d_q"].data_ptr(),
+                io["d_ids"].data_ptr(), io["d_scores"].data_ptr(), io["d_counts"].data_ptr(), io["h_ids"].data_ptr(),
+                io["h_scores"].data_ptr(), io["h_counts"].data_ptr(), self._stream()))
+            return io["h_ids"].clone(), io["h_scores"].clone(), io["h_counts"].clone()
 
     # two-step sharded search (exact-scores only the globally surviving documents)
     def shard_approx_keys(self, queries: torch.Tensor, params: FpbParams) -> torch.Tensor:

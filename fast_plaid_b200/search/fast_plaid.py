@@ -91,14 +91,17 @@ class FastPlaid:
         device: str | list[str] | None = None,
         low_memory: bool = True,
         shard: tuple[int, int] | str | None = None,
+        query_groups: int = 1,
         **kwargs: Any,  # noqa: ARG002
     ) -> None:
         """``index``/``device``/``low_memory`` as in the reference (fast_plaid.py:328-385).
 
         ``low_memory`` is accepted and ignored: a B200 holds the whole index in HBM.
-        ``shard``: ``(rank, world)`` makes this process own one contiguous document range and
-        merge with the other ranks through ``torch.distributed`` (NCCL); ``"auto"`` takes
-        rank/world from an initialised process group.
+        ``shard``: ``(rank, world)`` makes this process one rank of the document-sharded search (one
+        process per GPU; both exchanges are NCCL all-gathers issued below the C ABI, csrc/comm.cu);
+        ``"auto"`` takes rank/world from an initialised process group.  ``query_groups`` (a divisor of
+        world) arranges the ranks as query groups x document shards: each rank then holds
+        1 / (world / query_groups) of the documents and searches 1 / query_groups of every batch.
         """
         self.devices = self._resolve_devices(device)
 
@@ -109,8 +112,12 @@ class FastPlaid:
 
             shard = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else None
         self.shard: tuple[int, int] | None = shard  # type: ignore[assignment]
+        self.query_groups = int(query_groups)
+        self._comm = None
         if self.shard is not None and len(self.devices) != 1:
             raise ValueError("sharded mode is one process per GPU: pass exactly one device")
+        if self.shard is not None:
+            _engine.shard_grid(self.shard[0], self.shard[1], self.query_groups)  # validates the grid
 
         if not os.path.exists(self.index):
             os.makedirs(self.index, exist_ok=True)
@@ -123,6 +130,9 @@ class FastPlaid:
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
+        if getattr(self, "_comm", None) is not None:
+            self._comm.close()
+            self._comm = None
         with self._index_swap_lock:
             for idx in self.indices.values():
                 if idx is not None:
@@ -157,7 +167,8 @@ class FastPlaid:
         self._host_data = data if any(d == "cpu" for d in self.devices) else None
         base = 0
         if self.shard is not None:
-            data, base = _engine.shard_tensors(data, self.shard[0], self.shard[1])
+            _, doc_shard, n_shards = _engine.shard_grid(self.shard[0], self.shard[1], self.query_groups)
+            data, base = _engine.shard_tensors(data, doc_shard, n_shards)
 
         def provision(device: str):
             if device == "cpu":
@@ -454,6 +465,17 @@ class FastPlaid:
         ids, scores, counts = idx.search_host(queries, params)
         return _results_to_lists(ids, scores, counts)
 
+    def _shard_comm(self, idx: DeviceIndex):
+        """The NCCL communicator of the sharded search, created on first use (collective: every rank's first
+        sharded search creates it).  A world of one needs no process group."""
+        if self._comm is None:
+            rank, world = self.shard
+            if world == 1:
+                self._comm = _engine.ShardComm(1, 0, _engine.ShardComm.new_unique_id(), idx.device)
+            else:
+                self._comm = _engine.ShardComm.from_process_group(idx.device)
+        return self._comm
+
     def _search_sharded(self, idx: DeviceIndex, queries: torch.Tensor, params,
                         subset: list[list[int]] | None = None) -> list[list[tuple[int, float]]]:
         """Document-sharded search: local records -> NCCL all-gather -> global prune + rank."""
@@ -467,11 +489,21 @@ class FastPlaid:
                 out.copy_(t.unsqueeze(0))
             return out
 
+        rank, world = self.shard
+        if subset is None:
+            # the whole exchange below the C ABI: one call per batch, both all-gathers on the search stream
+            comm = self._shard_comm(idx)
+            if queries.device.type == "cpu" and queries.dtype.is_floating_point:
+                return _results_to_lists(*idx.search_sharded_host(comm, self.query_groups, queries, params))
+            q16 = queries.to(device=idx.device, dtype=torch.float16)
+            ids, scores, counts = idx.search_sharded(comm, self.query_groups, q16, params)
+            return _results_to_lists(ids.cpu(), scores.cpu(), counts.cpu())
+        if self.query_groups != 1:
+            raise NotImplementedError("subset= with query_groups > 1: use query_groups=1 (plain document sharding)")
         if queries.device.type == "cpu" and queries.dtype.is_floating_point:
             q16 = idx.stage_queries(queries, params.top_k)  # host cast (fast_plaid.py:241) + async H2D
         else:
             q16 = queries.to(device=idx.device, dtype=torch.float16, non_blocking=True)
-        rank, world = self.shard
         # step 1: local pruning, all-gather of the approximate-score keys
         if subset is None:
             keys = idx.shard_approx_keys(q16, params)
@@ -536,26 +568,49 @@ class FastPlaid:
     ) -> list[list[tuple[int, float, torch.Tensor]]]:
         """``search`` plus, per result, the ``[query_tokens, doc_tokens]`` fp16 similarity
         matrix (fast_plaid.py:985-1043, search.rs:668-686)."""
-        if self.shard is not None or len(self.devices) != 1:
-            raise NotImplementedError("search_token_scores runs on a single, unsharded device")
         base = self.search(queries_embeddings, top_k, batch_size, n_full_scores, n_ivf_probe, show_progress,
                            subset, n_processes)
-        _, queries, _ = self._prepare_search(queries_embeddings, None)
-        idx = self.indices[self.devices[0]]
+        search_indices, queries, _ = self._prepare_search(queries_embeddings, None)
+        # several devices in one process hold replicas: any of them can produce every matrix
+        idx = search_indices[self.devices[0]]
         q16 = queries.to(device=idx.device, dtype=torch.float16)
-        pairs_q, pairs_d = [], []
-        for b, res in enumerate(base):
-            for doc_id, _ in res:
-                pairs_q.append(b)
-                pairs_d.append(doc_id)
-        mats = idx.token_scores(q16, torch.tensor(pairs_q, dtype=torch.int32), torch.tensor(pairs_d, dtype=torch.int32))
-        lens = (idx.doc_offsets[1:] - idx.doc_offsets[:-1]).cpu()
+        pairs_q = torch.tensor([b for b, res in enumerate(base) for _ in res], dtype=torch.int64)
+        pairs_d = torch.tensor([d for res in base for d, _ in res], dtype=torch.int64)
+        n_pairs = int(pairs_d.shape[0])
+        lens_all = (idx.doc_offsets[1:] - idx.doc_offsets[:-1]).cpu()
+        if self.shard is None:
+            mats = idx.token_scores(q16, pairs_q.to(torch.int32), pairs_d.to(torch.int32))
+            lens = lens_all[pairs_d] if n_pairs else torch.zeros(0, dtype=torch.int64)
+        else:
+            # document-sharded: the rank that holds a document (in the first query group) computes its matrix
+            # (search.rs:668-686 on the owning shard); one all-reduce hands every matrix to every rank
+            import torch.distributed as dist
+
+            rank, world = self.shard
+            group, _, _ = _engine.shard_grid(rank, world, self.query_groups)
+            lo, hi = idx.doc_id_base, idx.doc_id_base + idx.num_documents
+            own = (pairs_d >= lo) & (pairs_d < hi) & (group == 0)
+            own_ix = own.nonzero().flatten()
+            mx = torch.tensor([max(idx.max_doc_len, 1)], dtype=torch.int64, device=idx.device)
+            if world > 1:
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            mats = torch.zeros((max(n_pairs, 1), int(mx), q16.shape[1]), dtype=torch.float16, device=idx.device)
+            lens_d = torch.zeros(max(n_pairs, 1), dtype=torch.int64, device=idx.device)
+            if own_ix.numel():
+                local = idx.token_scores(q16, pairs_q[own_ix].to(torch.int32), (pairs_d[own_ix] - lo).to(torch.int32))
+                mats[own_ix.to(idx.device), : local.shape[1]] = local
+                lens_d[own_ix.to(idx.device)] = lens_all[pairs_d[own_ix] - lo].to(idx.device)
+            if world > 1:
+                dist.all_reduce(mats, op=dist.ReduceOp.SUM)  # exactly one rank wrote each matrix, the others hold zeros
+                dist.all_reduce(lens_d, op=dist.ReduceOp.SUM)
+            lens = lens_d.cpu()
+        mats = mats.cpu()
         out, k = [], 0
         for res in base:
             row = []
             for doc_id, score in res:
-                n = int(lens[doc_id])
-                row.append((doc_id, score, mats[k, :n, :].transpose(0, 1).contiguous().cpu()))
+                n = int(lens[k])
+                row.append((doc_id, score, mats[k, :n, :].transpose(0, 1).contiguous()))
                 k += 1
             out.append(row)
         return out
@@ -581,7 +636,7 @@ class FastPlaid:
 
     @classmethod
     def from_device_index(cls, didx: DeviceIndex, index_dir: str | None = None,
-                          shard: tuple[int, int] | None = None) -> "FastPlaid":
+                          shard: tuple[int, int] | None = None, query_groups: int = 1) -> "FastPlaid":
         """A FastPlaid whose index is ALREADY resident in HBM (bench / serving processes that build or receive
         the tensors in memory): `search` runs the same code as for a directory-backed index -- reload check,
         query preparation, C-ABI call, result lists -- the directory only holds the `metadata.json` that check
@@ -594,6 +649,8 @@ class FastPlaid:
         os.makedirs(self.index, exist_ok=True)
         self.low_memory = False
         self.shard = shard
+        self.query_groups = int(query_groups)
+        self._comm = None
         meta_path = os.path.join(self.index, "metadata.json")
         if not os.path.exists(meta_path):
             with open(meta_path, "w") as f:

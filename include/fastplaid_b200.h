@@ -249,6 +249,38 @@ int fpb_shard_apply_threshold(const fpb_index* index, const uint64_t* d_all_keys
 int fpb_shard_exact_records(const fpb_index* index, int B, int Q, const fpb_params* params,
                             void* d_workspace, size_t workspace_bytes, fpb_record* d_records, void* stream);
 
+/* ---- the same exchange below the C ABI (fpb_comm_init / fpb_search_batch_sharded) ----
+ * An fpb_comm wraps one NCCL communicator (libnccl.so.2 is resolved at run time; without it these calls
+ * return FPB_ERR_UNSUPPORTED and everything else keeps working).  Rank 0 makes the id with
+ * fpb_comm_unique_id, the host distributes the FPB_COMM_ID_BYTES bytes by whatever means it has, every
+ * rank calls fpb_comm_create (collective).
+ *
+ * fpb_search_batch_sharded searches the WHOLE batch on a grid of  n_query_groups x (nranks/n_query_groups)
+ * document shards: rank r holds document shard r % n_shards (contiguous range, `doc_id_base` of its index)
+ * and searches the queries of group r / n_shards (B split into n_query_groups contiguous slices).  Both
+ * ncclAllGather calls (approximate-score keys, then the records of the globally surviving documents) are
+ * issued on `stream` from inside the call; every rank returns the result of every query.
+ *   d_queries  f16 [B, Q, dim]  the same batch on every rank
+ *   d_ws       workspace of fpb_workspace_layout(index, ceil(B / n_query_groups), Q, params)
+ *   d_scratch  fpb_sharded_scratch_bytes(ceil(B / n_query_groups), n_full_scores / 4, nranks) bytes */
+#define FPB_COMM_ID_BYTES 128
+typedef struct fpb_comm fpb_comm;
+int fpb_comm_unique_id(void* out_id /* FPB_COMM_ID_BYTES */);
+int fpb_comm_create(fpb_comm** out, int nranks, int rank, const void* unique_id, int device);
+void fpb_comm_destroy(fpb_comm* comm);
+int fpb_comm_nccl_version(void); /* 0 when NCCL is not loadable */
+int64_t fpb_sharded_scratch_bytes(int b_local, int R, int nranks);
+int fpb_search_batch_sharded(const fpb_index* index, fpb_comm* comm, int n_query_groups, const void* d_queries,
+                             int B, int Q, const fpb_params* params, void* d_workspace, size_t workspace_bytes,
+                             void* d_scratch, size_t scratch_bytes, int64_t* d_out_ids, float* d_out_scores,
+                             int32_t* d_out_counts, void* stream);
+/* The same with HOST buffers (H2D of the queries, D2H of the results, stream synchronise inside). */
+int fpb_search_batch_sharded_host(const fpb_index* index, fpb_comm* comm, int n_query_groups, const void* h_queries,
+                                  int B, int Q, const fpb_params* params, void* d_workspace, size_t workspace_bytes,
+                                  void* d_scratch, size_t scratch_bytes, void* d_queries_staging, int64_t* d_out_ids,
+                                  float* d_out_scores, int32_t* d_out_counts, int64_t* h_out_ids, float* h_out_scores,
+                                  int32_t* h_out_counts, void* stream);
+
 /* ---- by-products of the MaxSim kernel ("next" rows of SURVEY.md 8f-3) ---- */
 /* reconstruct_embeddings (rust/utils/embeddings.rs:12-69): decompressed, normalised
  * fp16 rows of the given local docs, concatenated.  d_out: f16 [sum(len), dim]. */

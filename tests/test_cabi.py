@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(engine.EXPORTED_SYMBOLS) == declared, "engine.EXPORTED_SYMBOLS is out of sync with the header"
-    assert lib.fpb_abi_version() == 4
+    assert lib.fpb_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header():

@@ -155,6 +155,43 @@ def test_two_shards_on_one_gpu_equal_the_unsharded_search(cuda_device):
             assert n_scored <= queries.shape[0] * (n_full // 4)  # exact-scored docs: at most R per query in total
 
 
+def test_one_rank_communicator_runs_the_sharded_c_path(cuda_device):
+    """fpb_comm_create with one rank + fpb_search_batch_sharded(_host): the whole exchange path (keys ->
+    ncclAllGather -> threshold -> MaxSim -> records -> ncclAllGather -> merge) on a single GPU, equal to
+    fpb_search_batch; also through FastPlaid(shard=(0, 1)).  Ragged batch: 5 queries."""
+    from fast_plaid_b200.engine import DeviceIndex, ShardComm
+    from fast_plaid_b200.search.fast_plaid import FastPlaid
+
+    docs = make_docs(500, 10, 60, seed=41)
+    oidx, _ = build_oracle_index(docs)
+    didx = DeviceIndex(to_index_tensors(oidx), cuda_device)
+    queries = make_queries(5, 32, seed=42, docs=docs)
+    q16 = queries.half().to(cuda_device)
+    comm = ShardComm(1, 0, ShardComm.new_unique_id(), cuda_device)
+    assert didx._lib.fpb_comm_nccl_version() > 0
+    for n_full, top_k in ((64, 10), (4096, 40)):
+        params = DeviceIndex.make_params(top_k, n_full, 8)
+        ids, scores, counts = didx.search(q16, params)
+        i2, s2, c2 = didx.search_sharded(comm, 1, q16, params)
+        torch.cuda.synchronize()
+        assert torch.equal(i2, ids) and torch.equal(s2, scores) and torch.equal(c2, counts)
+        h = didx.search_sharded_host(comm, 1, queries, params)
+        assert torch.equal(h[0], ids.cpu()) and torch.equal(h[1], scores.cpu()) and torch.equal(h[2], counts.cpu())
+    with pytest.raises(ValueError):
+        didx.search_sharded(comm, 2, q16, params)  # 2 query groups do not divide 1 rank
+    comm.close()
+    fp = FastPlaid.from_device_index(didx, shard=(0, 1))
+    plain = FastPlaid.from_device_index(didx)
+    assert fp.search(queries, top_k=10) == plain.search(queries, top_k=10)
+    # token-score matrices through the sharded surface (the owning rank computes, search.rs:668-686)
+    a_ts = fp.search_token_scores(queries, top_k=4)
+    b_ts = plain.search_token_scores(queries, top_k=4)
+    for ra, rb in zip(a_ts, b_ts):
+        assert [(d, s_) for d, s_, _ in ra] == [(d, s_) for d, s_, _ in rb]
+        assert all(torch.equal(ma, mb) for (_, _, ma), (_, _, mb) in zip(ra, rb))
+    fp.close()
+
+
 def test_sharded_subset_search_equals_the_unsharded_subset_search(cuda_device):
     """subset= with documents sharded: the centroid bitmaps of the shards are OR-ed (the all-gather is
     emulated by stacking, all shards live on one device) and the result must equal the single-index

@@ -1,6 +1,8 @@
-"""Two-GPU test of the document-sharded path over NCCL (skipped with fewer than 2 GPUs):
-per-shard fpb_search_shard -> all_gather_into_tensor -> fpb_merge_shards on every rank must
-equal the unsharded fpb_search_batch bit for bit."""
+"""Multi-GPU tests of the document-sharded path over NCCL (skipped with fewer than 2 GPUs): the step-wise
+exchange (fpb_search_shard / fpb_shard_* + all_gather_into_tensor + fpb_merge_shards) and the one-call
+fpb_search_batch_sharded (ncclAllGather issued below the C ABI, every query-group x document-shard grid) must
+equal the unsharded fpb_search_batch bit for bit on every rank.  The one-rank form of the C path runs on a
+single GPU in tests/test_gpu_api.py."""
 
 from __future__ import annotations
 
@@ -81,6 +83,32 @@ def _worker(rank: int, world: int, port: int, out):
         for b in range(queries.shape[0]):
             n = int(c4[b])
             ok = ok and torch.equal(i5[b, :n], i4[b, :n]) and torch.equal(s5[b, :n], s4[b, :n])
+        # the same exchange below the C ABI: one call, both ncclAllGather issued inside (csrc/comm.cu), on every
+        # grid of query groups x document shards the world allows
+        from fast_plaid_b200.engine import ShardComm, shard_grid
+
+        if "comm" not in locals():
+            comm = ShardComm.from_process_group(dev)
+        for n_groups in [g for g in (1, 2, 4) if world % g == 0]:
+            _, d_shard, n_shards = shard_grid(rank, world, n_groups)
+            sh_g, base_g = shard_tensors(t, d_shard, n_shards)
+            part = DeviceIndex(sh_g, dev, doc_id_base=base_g)
+            i6, s6, c6 = part.search_sharded(comm, n_groups, queries, params)
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(i6, ids) and torch.equal(s6, scores) and torch.equal(c6, counts)
+            h = part.search_sharded_host(comm, n_groups, queries.float().cpu(), params)
+            ok = ok and torch.equal(h[0], ids.cpu()) and torch.equal(h[1], scores.cpu())
+    # the FastPlaid surface in sharded mode: search and search_token_scores (matrices computed by the owning rank)
+    from fast_plaid_b200.search.fast_plaid import FastPlaid
+
+    fp_sh = FastPlaid.from_device_index(mine, shard=(rank, world))
+    fp_w = FastPlaid.from_device_index(whole)
+    qh = queries.float().cpu()
+    ok = ok and fp_sh.search(qh, top_k=7) == fp_w.search(qh, top_k=7)
+    ts_a, ts_b = fp_sh.search_token_scores(qh, top_k=4), fp_w.search_token_scores(qh, top_k=4)
+    for ra, rb in zip(ts_a, ts_b):
+        ok = ok and [(d, s_) for d, s_, _ in ra] == [(d, s_) for d, s_, _ in rb]
+        ok = ok and all(torch.equal(ma, mb) for (_, _, ma), (_, _, mb) in zip(ra, rb))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -90,13 +118,16 @@ def _worker(rank: int, world: int, port: int, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_nccl_sharded_search_equals_unsharded():
+@pytest.mark.parametrize("world", [2, 4])
+def test_nccl_sharded_search_equals_unsharded(world):
     import torch.multiprocessing as mp
 
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=600)

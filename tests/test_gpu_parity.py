@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from util import (build_oracle_index, fp16_ulp_diff, make_docs, make_queries, oracle_exact_scores,
-                  ranking_consistent, to_index_tensors)
+                  oracle_token_matrix, ranking_consistent, to_index_tensors)
 
 from oracle import plaid_oracle as po
 
@@ -264,6 +264,35 @@ def test_reconstruct_matches_oracle(cuda_device):
         bad += int((dlt > 0).sum())
         tot += dlt.numel()
     assert bad / tot < 5e-3
+
+
+@pytest.mark.parametrize("name", ["base", "ragged_short", "q64", "nbits2", "dim64"])
+def test_token_score_matrices_match_the_oracle(name, cuda_device):
+    """fpb_token_scores (search.rs:668-686) against the oracle's token matrices for the documents the engine
+    returns: every entry within one fp16 ulp, almost all identical (the two sides accumulate the 128 products
+    of a dot product in different orders), and max-over-tokens / sum-over-query-tokens of the GPU matrix equals
+    the score the search returned (tests/test.py:175-197 asserts 0.1; here 1e-3)."""
+    oidx, didx, queries, params, st = _setup(name, cuda_device)
+    B, Q = queries.shape[0], queries.shape[1]
+    q16 = queries.half().to(cuda_device)
+    pairs = [(b, int(d)) for b in range(B) for d in st["ids"][b, : int(st["counts"][b])].tolist()]
+    mats = didx.token_scores(q16, torch.tensor([p[0] for p in pairs], dtype=torch.int32),
+                             torch.tensor([p[1] for p in pairs], dtype=torch.int32)).cpu()
+    torch.cuda.synchronize()
+    bad = tot = 0
+    for k, (b, d) in enumerate(pairs):
+        ref = oracle_token_matrix(oidx, queries[b], d)  # [Q, len]
+        n = ref.shape[1]
+        got = mats[k, :n, :].transpose(0, 1)
+        dlt = fp16_ulp_diff(got, ref)
+        assert int(dlt.max()) <= 1, f"pair {k}: token scores differ by {int(dlt.max())} fp16 ulps"
+        bad += int((dlt > 0).sum())
+        tot += dlt.numel()
+        assert float(mats[k, n:, :].abs().max() if mats.shape[1] > n else 0.0) == 0.0  # rows past the document stay zero
+        rank = st["ids"][b, : int(st["counts"][b])].tolist().index(d)
+        manual = float(got.float().max(dim=1).values.sum())
+        assert abs(manual - float(st["scores"][b, rank])) <= 1e-3 * max(1.0, abs(manual))
+    assert bad / max(tot, 1) < 5e-3, f"{bad}/{tot} token scores differ by one ulp"
 
 
 def test_compress_only_index_refuses_search(cuda_device):

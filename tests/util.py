@@ -83,6 +83,19 @@ def oracle_exact_scores(oidx, query: torch.Tensor, doc_ids: list[int]) -> torch.
     return plaid_oracle.colbert_score_reduce(ts, mask)
 
 
+def oracle_token_matrix(oidx, query: torch.Tensor, doc_id: int) -> torch.Tensor:
+    """Reference token-score matrix (search.rs:651-655 then :668-686) of one document: fp16 [Q, len]."""
+    sel = torch.tensor([doc_id], dtype=torch.int64)
+    codes, lens = plaid_oracle.ragged_lookup(oidx.doc_codes, oidx.doc_offsets, oidx.doc_lengths, sel)
+    res, _ = plaid_oracle.ragged_lookup(oidx.doc_residuals, oidx.doc_offsets, oidx.doc_lengths, sel)
+    emb = plaid_oracle.decompress_residuals(res, oidx.bucket_weights, oidx.byte_reversed_bits_map,
+                                            oidx.bucket_weight_indices_lookup, codes, oidx.centroids, oidx.dim,
+                                            oidx.nbits)
+    padded, _ = plaid_oracle.direct_pad_sequences(emb, lens, 0.0)
+    ts = padded.matmul(query.half().unsqueeze(0).transpose(-2, -1))  # [1, len, Q]
+    return ts[0, : int(lens[0])].transpose(0, 1).contiguous()
+
+
 def ranking_consistent(gpu_ids, gpu_scores, ref_score_of: dict, tol: float, fallback=None) -> tuple[bool, str]:
     """The GPU ranking must be a valid ranking of the reference scores up to `tol`:
     every returned doc has (nearly) the reference score, and no doc is ranked above another
