@@ -82,9 +82,14 @@ __device__ __forceinline__ uint32_t en_sw_off(int r, int c) {
 }
 
 
+// KMEANS = false: code = argmax_k fp16(<x, c_k>)                      (index-build encode)
+// KMEANS = true : code = argmax_k (<x, c_k> + bias[k]) in fp32, bias[k] = -|c_k|^2 / 2, i.e. the nearest centroid
+//                 by squared distance (the assignment step of Lloyd's algorithm, kmeans.py:153-160)
+template <bool KMEANS>
 __global__ void __launch_bounds__(EN_THREADS, 1)
 encode_assign_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const __half* __restrict__ X, int64_t n,
-                     int32_t* __restrict__ codes, int n_ctiles) {
+                     int32_t* __restrict__ codes, int n_ctiles, const float* __restrict__ bias) {
+  __shared__ float s_bias[4][2][128];  // per epilogue warp and accumulator: the tile's biases
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t dyn_addr = smem_u32(smem_dyn);
   unsigned char* base = smem_dyn + ((1024u - (dyn_addr & 1023u)) & 1023u);
@@ -184,6 +189,14 @@ encode_assign_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const __
         const int acc = g & 1;
         const int k0 = i * 128;
         const int rows_valid = min(128, K - k0);
+        if (KMEANS) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int kk = k0 + x * 32 + lane;
+            s_bias[warp][acc][x * 32 + lane] = kk < K ? __ldg(bias + kk) : 0.f;
+          }
+          __syncwarp();
+        }
         en_mbar_wait(bar_tfull + 8 * acc, (g >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -192,8 +205,9 @@ encode_assign_kernel(const __grid_constant__ CUtensorMap tmap_c, int K, const __
           en_tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + acc * 128 + c0, r);
 #pragma unroll
           for (int x = 0; x < 32; ++x) {
-            // the reference compares fp16 scores (half matmul output); first maximum wins
-            const float v = __half2float(__float2half_rn(__uint_as_float(r[x])));
+            // encode: the reference compares fp16 scores (half matmul output); first maximum wins
+            const float v = KMEANS ? __uint_as_float(r[x]) + s_bias[warp][acc][c0 + x]
+                                   : __half2float(__float2half_rn(__uint_as_float(r[x])));
             if (c0 + x < rows_valid && v > best) {
               best = v;
               best_k = k0 + c0 + x;
@@ -256,6 +270,119 @@ typedef CUresult (*en_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint
 
 }  // namespace
 
+// tensor map of the centroid table + launch of the assign kernel (shared by fpb_encode and fpb_kmeans_assign)
+static int launch_assign(int device, int64_t n_centroids, const void* d_centroids, const void* d_tokens,
+                         int64_t n_tokens, int32_t* d_codes, const float* d_bias, cudaStream_t st, const char* who) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    fpb_set_error("%s: cuTensorMapEncodeTiled is not available from this driver", who);
+    return FPB_ERR_CUDA;
+  }
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {128, cuuint64_t(n_centroids)};
+  const cuuint64_t gstride[1] = {256};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  if (reinterpret_cast<en_encode_tiled_fn>(fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_centroids),
+                                               gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    fpb_set_error("%s: cuTensorMapEncodeTiled failed", who);
+    return FPB_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  FPB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  const int64_t n_ttiles = (n_tokens + 127) / 128;
+  const int blocks = int(n_ttiles < prop.multiProcessorCount ? n_ttiles : prop.multiProcessorCount);
+  const int n_ctiles = int((n_centroids + 127) / 128);
+  // opt in on every launch: the attribute is per device and the call costs about a microsecond
+  if (d_bias) {
+    FPB_CUDA_CHECK(cudaFuncSetAttribute(encode_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EnSmem::bytes));
+    encode_assign_kernel<true><<<blocks, EN_THREADS, EnSmem::bytes, st>>>(tm, int(n_centroids),
+                                                                         static_cast<const __half*>(d_tokens), n_tokens,
+                                                                         d_codes, n_ctiles, d_bias);
+  } else {
+    FPB_CUDA_CHECK(cudaFuncSetAttribute(encode_assign_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EnSmem::bytes));
+    encode_assign_kernel<false><<<blocks, EN_THREADS, EnSmem::bytes, st>>>(tm, int(n_centroids),
+                                                                          static_cast<const __half*>(d_tokens), n_tokens,
+                                                                          d_codes, n_ctiles, nullptr);
+  }
+  FPB_LAUNCH_CHECK("encode_assign");
+  return FPB_OK;
+}
+
+// Centroid update of Lloyd's algorithm as a deterministic segmented mean: `order` lists the point indices sorted by
+// assigned centroid, `seg_offsets[k] .. seg_offsets[k+1]` is centroid k's segment.  One warp per centroid, each lane
+// sums four dimensions in fp32 in segment order; empty segments leave the output row untouched and count 0.
+__global__ void __launch_bounds__(256)
+segment_mean_kernel(const __half* __restrict__ X, const int64_t* __restrict__ order,
+                    const int64_t* __restrict__ seg_offsets, int64_t K, __half* __restrict__ out,
+                    float* __restrict__ shift) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (k >= K) return;
+  const int64_t s0 = seg_offsets[k], s1 = seg_offsets[k + 1];
+  if (s1 <= s0) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int64_t i = s0; i < s1; ++i) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(X + order[i] * 128) + lane);
+    const float2 f0 = __half22float2(u32_as_half2(v.x)), f1 = __half22float2(u32_as_half2(v.y));
+    a0 += f0.x; a1 += f0.y; a2 += f1.x; a3 += f1.y;
+  }
+  const float inv = 1.0f / float(s1 - s0);
+  const __half2 h0 = __floats2half2_rn(a0 * inv, a1 * inv), h1 = __floats2half2_rn(a2 * inv, a3 * inv);
+  uint2* dst = reinterpret_cast<uint2*>(out + k * 128) + lane;
+  if (shift) {  // |new - old| of this centroid, for the convergence test (kmeans.py:213-218)
+    const uint2 old = *dst;
+    const float2 o0 = __half22float2(u32_as_half2(old.x)), o1 = __half22float2(u32_as_half2(old.y));
+    const float2 n0 = __half22float2(h0), n1 = __half22float2(h1);
+    float d = (n0.x - o0.x) * (n0.x - o0.x) + (n0.y - o0.y) * (n0.y - o0.y) + (n1.x - o1.x) * (n1.x - o1.x) +
+              (n1.y - o1.y) * (n1.y - o1.y);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if (lane == 0) shift[k] = sqrtf(d);
+  }
+  *dst = make_uint2(half2_as_u32(h0), half2_as_u32(h1));
+}
+
+extern "C" int fpb_kmeans_assign(int device, int dim, int64_t n_centroids, const void* d_centroids,
+                                 const float* d_bias, const void* d_points, int64_t n_points, int32_t* d_assign,
+                                 void* stream) {
+  if (dim != 128) {
+    fpb_set_error("fpb_kmeans_assign: this build handles dim=128 (got %d)", dim);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  if (!d_centroids || !d_bias || !d_points || !d_assign || n_centroids < 1 || n_points < 0) {
+    fpb_set_error("fpb_kmeans_assign: bad arguments");
+    return FPB_ERR_INVALID;
+  }
+  if (n_points == 0) return FPB_OK;
+  FPB_CUDA_CHECK(cudaSetDevice(device));
+  return launch_assign(device, n_centroids, d_centroids, d_points, n_points, d_assign, d_bias,
+                       static_cast<cudaStream_t>(stream), "fpb_kmeans_assign");
+}
+
+extern "C" int fpb_kmeans_update(int device, int dim, int64_t n_centroids, const void* d_points,
+                                 const int64_t* d_order, const int64_t* d_seg_offsets, void* d_centroids,
+                                 float* d_shift, void* stream) {
+  if (dim != 128) {
+    fpb_set_error("fpb_kmeans_update: this build handles dim=128 (got %d)", dim);
+    return FPB_ERR_UNSUPPORTED;
+  }
+  if (!d_points || !d_order || !d_seg_offsets || !d_centroids || n_centroids < 1) {
+    fpb_set_error("fpb_kmeans_update: bad arguments");
+    return FPB_ERR_INVALID;
+  }
+  FPB_CUDA_CHECK(cudaSetDevice(device));
+  segment_mean_kernel<<<unsigned((n_centroids + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(d_points), d_order, d_seg_offsets, n_centroids, static_cast<__half*>(d_centroids),
+      d_shift);
+  FPB_LAUNCH_CHECK("segment_mean");
+  return FPB_OK;
+}
+
 extern "C" int fpb_encode(int device, int nbits, int dim, int64_t n_centroids, const void* d_centroids,
                           const void* d_tokens, int64_t n_tokens, const float* d_cutoffs, int32_t* d_codes,
                           uint8_t* d_residuals, void* stream) {
@@ -270,36 +397,10 @@ extern "C" int fpb_encode(int device, int nbits, int dim, int64_t n_centroids, c
   if (n_tokens == 0) return FPB_OK;
   FPB_CUDA_CHECK(cudaSetDevice(device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-      qres != cudaDriverEntryPointSuccess) {
-    fpb_set_error("fpb_encode: cuTensorMapEncodeTiled is not available from this driver");
-    return FPB_ERR_CUDA;
+  {
+    const int rc = launch_assign(device, n_centroids, d_centroids, d_tokens, n_tokens, d_codes, nullptr, st, "fpb_encode");
+    if (rc != FPB_OK) return rc;
   }
-  CUtensorMap tm;
-  const cuuint64_t gdim[2] = {128, cuuint64_t(n_centroids)};
-  const cuuint64_t gstride[1] = {256};
-  const cuuint32_t box[2] = {64, 128};
-  const cuuint32_t estr[2] = {1, 1};
-  if (reinterpret_cast<en_encode_tiled_fn>(fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_centroids),
-                                               gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-    fpb_set_error("fpb_encode: cuTensorMapEncodeTiled failed");
-    return FPB_ERR_CUDA;
-  }
-  // opt in on every launch: the attribute is per device and the call costs about a microsecond
-  FPB_CUDA_CHECK(cudaFuncSetAttribute(encode_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EnSmem::bytes));
-  cudaDeviceProp prop;
-  FPB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-  const int64_t n_ttiles = (n_tokens + 127) / 128;
-  const int blocks = int(n_ttiles < prop.multiProcessorCount ? n_ttiles : prop.multiProcessorCount);
-  const int n_ctiles = int((n_centroids + 127) / 128);
-  encode_assign_kernel<<<blocks, EN_THREADS, EnSmem::bytes, st>>>(tm, int(n_centroids),
-                                                                 static_cast<const __half*>(d_tokens), n_tokens, d_codes,
-                                                                 n_ctiles);
-  FPB_LAUNCH_CHECK("encode_assign");
   const int pd = dim * nbits / 8;
   const int64_t total = n_tokens * pd;
   const int pblocks = int(((total + 255) / 256) < 65535 * 16 ? ((total + 255) / 256) : 65535 * 16);

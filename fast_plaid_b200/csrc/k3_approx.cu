@@ -389,11 +389,24 @@ k3_hibits_kernel(const __half* __restrict__ S, int64_t K, const __half* __restri
   if (lane == 0) hibits[int64_t(b) * hb_words + word] = w;
 }
 
-// step 3: the bound pass.  Shared memory: the query's K-bit map, one K3_WQ-entry ring of high codes per warp, and the
-// offsets / lengths of the chunk's documents (staged by the first K3A_DOCS_PER_CHUNK threads so that the dependent
+// step 3: the bound pass.  Shared memory: the query's K-bit map, one ring of high codes per warp, and the offsets /
+// lengths of the chunk's documents (staged by the first K3A_DOCS_PER_CHUNK threads so that the dependent
 // candidate -> offset loads are paid once per chunk, not once per document).  A warp walks its documents as a stream
-// of 128-token groups and always has the NEXT group's code loads in flight while it tests, queues and gathers the
-// current one: the pass is otherwise a chain of dependent latencies (codes from HBM, then the gathers from L2).
+// of W-window groups and always has the NEXT group's code loads in flight while it tests, queues and gathers the
+// current one.  The first version of this kernel was ISSUE-bound (profiles/r02_k3_bound_v1_raw.csv: 15.3 G warp
+// instructions, 91 per 32-token window, issue slots 81 % busy; a third of them branches and generic-address
+// arithmetic around the shared-memory accesses), so the per-window path is written branch-free with explicit 32-bit
+// shared addresses: predicated code load, one LDS of the bitmap word, a wrap-around funnel shift for the bit, ballot,
+// predicated STS into the ring.  Tokens outside the document carry the code K3_INV whose bit is a spare zero word.
+__device__ __forceinline__ uint32_t k3_lds(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void k3_sts_if(uint32_t addr, uint32_t v, uint32_t pred) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
+}
+
 template <int LPR, int MINB, int W, int U>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
@@ -402,24 +415,26 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
                 const __half* __restrict__ tau, const uint32_t* __restrict__ hibits, int hb_words,
                 float* __restrict__ ub_out, float* __restrict__ lb_out, unsigned long long* __restrict__ stats) {
   constexpr int QP = LPR * 8;
-  constexpr int TPI = 32 / LPR;          // rows per warp-wide gather
-  constexpr int FLUSH = U * TPI;         // rows per flush (<= 64)
+  constexpr int TPI = 32 / LPR;   // rows per warp-wide gather
+  constexpr int FLUSH = U * TPI;  // rows per batch of gathers (<= 64)
   constexpr int DPW = K3A_DOCS_PER_CHUNK / (K3_THREADS / 32);  // documents per warp and chunk
   constexpr int WQ = K3_WQ_FOR(W, FLUSH);  // ring entries per warp: one group of pushes on top of an unflushed rest
   static_assert(FLUSH + 32 * W <= WQ, "ring too small");
-  extern __shared__ __align__(16) uint32_t k3_smem[];
-  uint32_t* bm = k3_smem;
+  extern __shared__ __align__(16) uint32_t k3_smem[];  // [hb_words + 4] bitmap (+ a zero word) | [warps][WQ] rings
   __shared__ int s_b, s_c;
   __shared__ int64_t s_o0[K3A_DOCS_PER_CHUNK];
   __shared__ int s_len[K3A_DOCS_PER_CHUNK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane % LPR, grp = lane / LPR;
-  int32_t* wq = reinterpret_cast<int32_t*>(k3_smem + hb_words) + warp * WQ;
+  const uint32_t sb_bm = smem_u32(k3_smem);
+  const uint32_t sb_wq = sb_bm + uint32_t(hb_words + 4) * 4u + uint32_t(warp) * (WQ * 4u);
+  const int INV = hb_words * 32;  // a code whose bit lives in the spare zero word
   unsigned lt_mask;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
   const __half2 sentinel = __float2half2_rn(FPB_PAD_SENTINEL);
   unsigned rows = 0, toks = 0;  // per warp over the CTA's life: far below 2^32
   int cur_b = -1;
+  if (tid < 4) k3_smem[hb_words + tid] = 0u;  // never overwritten: the bitmap copy below covers hb_words words
 
   for (;;) {
     k3_next_chunk(work, B, &s_b, &s_c);
@@ -441,7 +456,7 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
     }
     if (b != cur_b) {  // CTA-uniform; every warp is past the previous chunk (barrier in k3_next_chunk)
       const uint4* src = reinterpret_cast<const uint4*>(hibits + int64_t(b) * hb_words);
-      for (int i = tid; i < hb_words / 4; i += K3_THREADS) reinterpret_cast<uint4*>(bm)[i] = src[i];
+      for (int i = tid; i < hb_words / 4; i += K3_THREADS) reinterpret_cast<uint4*>(k3_smem)[i] = src[i];
       cur_b = b;
     }
     __syncthreads();
@@ -453,66 +468,68 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
     const int slot_end = slot + DPW;
     int len = s_len[slot];
     if (len < 0) continue;  // warp-uniform: this warp has no document in the (last, partial) chunk
-    int lo, hi, f0 = 0;
+    // rel = index inside the document of this lane's token in window 0 of the group (negative before the start);
+    // nwin = windows of the frame [0, lo + len) aligned to absolute multiples of 32 tokens (one 128-byte line each)
+    int rel, left;  // left = windows of the document not yet walked (including the current group's)
     const int32_t* cw;
     {
       const int64_t o0 = s_o0[slot];
-      const int64_t w0 = o0 & ~int64_t(31);  // frame aligned to an absolute multiple of 32 tokens: one 128-byte line per window
-      lo = int(o0 - w0);
-      hi = lo + len;
-      cw = codes + w0 + lane;
+      const int lo = int(o0 & 31);
+      rel = lane - lo;
+      left = (lo + len + 31) >> 5;
+      cw = codes + (o0 - lo) + lane;
     }
     int c[W];
 #pragma unroll
     for (int u = 0; u < W; ++u) {
-      const int f = u * 32 + lane;
-      c[u] = (f >= lo && f < hi) ? __ldg(cw + u * 32) : -1;
+      c[u] = INV;
+      if (unsigned(rel + 32 * u) < unsigned(len)) c[u] = __ldg(cw + 32 * u);
     }
-    int head = 0, tail = 0;
+    uint32_t head = 0, tail = 0;
     __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
 
     for (;;) {
       // ---- the next group: same document or the next slot; its code loads go out now ----
-      int nslot = slot, nf0 = f0 + 32 * W, nlen = len, nlo = lo, nhi = hi;
-      const int32_t* ncw = cw;
-      const bool last_of_doc = nf0 >= hi;
+      const bool last_of_doc = left <= W;
+      int nlen = len, nrel = rel + 32 * W, nleft = left - W;
+      const int32_t* ncw = cw + 32 * W;
       if (last_of_doc) {
-        nslot = slot + 1;
-        nf0 = 0;
-        nlen = nslot < slot_end ? s_len[nslot] : -1;
+        nlen = (slot + 1 < slot_end) ? s_len[slot + 1] : -1;
         if (nlen >= 0) {
-          const int64_t o0 = s_o0[nslot];
-          const int64_t w0 = o0 & ~int64_t(31);
-          nlo = int(o0 - w0);
-          nhi = nlo + nlen;
-          ncw = codes + w0 + lane;
+          const int64_t o0 = s_o0[slot + 1];
+          const int lo = int(o0 & 31);
+          nrel = lane - lo;
+          nleft = (lo + nlen + 31) >> 5;
+          ncw = codes + (o0 - lo) + lane;
         }
       }
       int nx[W];
+      {
+        const unsigned nlen_u = nlen < 0 ? 0u : unsigned(nlen);
 #pragma unroll
-      for (int u = 0; u < W; ++u) {
-        const int f = nf0 + u * 32 + lane;
-        nx[u] = (nlen >= 0 && f >= nlo && f < nhi) ? __ldg(ncw + nf0 + u * 32) : -1;
-      }
-      // ---- current group: test the bit of every token (independent shared-memory reads), queue the high codes,
-      //      then gather in full batches ----
-      bool bit[W];
-#pragma unroll
-      for (int u = 0; u < W; ++u) bit[u] = c[u] >= 0 && ((bm[c[u] >> 5] >> (c[u] & 31)) & 1u);
-#pragma unroll
-      for (int u = 0; u < W; ++u) {
-        if (f0 + u * 32 < hi) {  // warp-uniform
-          const unsigned mask = __ballot_sync(0xffffffffu, bit[u]);
-          if (bit[u]) wq[(tail + __popc(mask & lt_mask)) & (WQ - 1)] = c[u];
-          tail += __popc(mask);
+        for (int u = 0; u < W; ++u) {
+          nx[u] = INV;
+          if (unsigned(nrel + 32 * u) < nlen_u) nx[u] = __ldg(ncw + 32 * u);
         }
       }
+      // ---- current group: bit of every token (W independent shared loads), queue the high codes ----
+      uint32_t wbit[W];
+#pragma unroll
+      for (int u = 0; u < W; ++u) wbit[u] = k3_lds(sb_bm + ((uint32_t(c[u]) >> 5) << 2));
+#pragma unroll
+      for (int u = 0; u < W; ++u) {
+        const uint32_t bit = __funnelshift_r(wbit[u], 0u, uint32_t(c[u])) & 1u;  // shift by c mod 32
+        const unsigned mask = __ballot_sync(0xffffffffu, bit != 0u);
+        k3_sts_if(sb_wq + (((tail + __popc(mask & lt_mask)) & (WQ - 1)) << 2), uint32_t(c[u]), bit);
+        tail += __popc(mask);
+      }
       __syncwarp();
+      // ---- gather in full batches ----
       while (tail - head >= FLUSH) {
         uint4 v[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-          const int code = wq[(head + k * TPI + grp) & (WQ - 1)];
+          const uint32_t code = k3_lds(sb_wq + (((head + k * TPI + grp) & (WQ - 1)) << 2));
           v[k] = __ldg(Sb + int64_t(code) * LPR);
         }
 #pragma unroll
@@ -524,18 +541,17 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
         }
         head += FLUSH;
       }
-      __syncwarp();
       if (last_of_doc) {
         {  // drain: fewer than FLUSH codes left
-          const int rem = tail - head;
+          const uint32_t rem = tail - head;
           uint4 v[U];
 #pragma unroll
           for (int k = 0; k < U; ++k) {
-            const int jj = k * TPI + grp;
+            const uint32_t jj = k * TPI + grp;
             v[k] = make_uint4(half2_as_u32(sentinel), half2_as_u32(sentinel), half2_as_u32(sentinel),
                               half2_as_u32(sentinel));
             if (jj < rem) {
-              const int code = wq[(head + jj) & (WQ - 1)];
+              const uint32_t code = k3_lds(sb_wq + (((head + jj) & (WQ - 1)) << 2));
               v[k] = __ldg(Sb + int64_t(code) * LPR);
             }
           }
@@ -546,9 +562,8 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
             m2 = __hmax2(m2, u32_as_half2(v[k].z));
             m3 = __hmax2(m3, u32_as_half2(v[k].w));
           }
-          __syncwarp();  // the next document's pushes may reuse these slots
         }
-        rows += unsigned(tail);
+        rows += tail;
         toks += unsigned(len);
         k3_reduce_groups<LPR>(m0, m1, m2, m3);
         // lower bound: the maxima over the gathered rows; upper bound: unresolved columns raised to tau
@@ -575,14 +590,14 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
         if (nlen < 0) break;  // no further document for this warp in the chunk
         head = tail = 0;
         m0 = m1 = m2 = m3 = sentinel;
+        ++slot;
       }
+      __syncwarp();  // the ring slots read above may be overwritten by the next group's pushes
 #pragma unroll
       for (int u = 0; u < W; ++u) c[u] = nx[u];
-      slot = nslot;
-      f0 = nf0;
       len = nlen;
-      lo = nlo;
-      hi = nhi;
+      rel = nrel;
+      left = nleft;
       cw = ncw;
     }
   }
@@ -1105,11 +1120,12 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
     constexpr int TPI = 32 / LPR;
     switch (shape) {
       case 1: kern = k3_bound_kernel<LPR, 5, 4, 4>; minb = 5; wq = K3_WQ_FOR(4, 4 * TPI); break;
-      case 2: kern = k3_bound_kernel<LPR, 3, 12, 8>; minb = 3; wq = K3_WQ_FOR(12, 8 * TPI); break;
-      case 3: kern = k3_bound_kernel<LPR, 4, 6, 8>; minb = 4; wq = K3_WQ_FOR(6, 8 * TPI); break;
-      default: kern = k3_bound_kernel<LPR, 4, 12, 4>; minb = 4; wq = K3_WQ_FOR(12, 4 * TPI); break;
+      case 2: kern = k3_bound_kernel<LPR, 4, 12, 4>; minb = 4; wq = K3_WQ_FOR(12, 4 * TPI); break;
+      case 3: kern = k3_bound_kernel<LPR, 4, 8, 4>; minb = 4; wq = K3_WQ_FOR(8, 4 * TPI); break;
+      case 4: kern = k3_bound_kernel<LPR, 5, 6, 4>; minb = 5; wq = K3_WQ_FOR(6, 4 * TPI); break;
+      default: kern = k3_bound_kernel<LPR, 4, 6, 4>; minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
     }
-    const size_t smem = size_t(L.hb_words) * 4 + size_t(K3_THREADS / 32) * wq * 4;
+    const size_t smem = size_t(L.hb_words + 4) * 4 + size_t(K3_THREADS / 32) * wq * 4;
     FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)
     int per_sm = int((227 * 1024) / (smem + 1024 + 2048));

@@ -130,6 +130,8 @@ EXPORTED_SYMBOLS = [
     "fpb_reconstruct",
     "fpb_token_scores",
     "fpb_encode",
+    "fpb_kmeans_assign",
+    "fpb_kmeans_update",
     "fpb_cast_f32_to_f16_host",
     "fpb_cast_f32_to_f16_host_portable",
 ]
@@ -224,6 +226,10 @@ def load_library() -> ctypes.CDLL:
             fn.argtypes = [vp, vp, sz]
         lib.fpb_encode.restype = i32
         lib.fpb_encode.argtypes = [i32, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp]
+        lib.fpb_kmeans_assign.restype = i32
+        lib.fpb_kmeans_assign.argtypes = [i32, i32, i64, vp, vp, vp, i64, vp, vp]
+        lib.fpb_kmeans_update.restype = i32
+        lib.fpb_kmeans_update.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, vp]
         lib.fpb_token_scores.restype = i32
         lib.fpb_token_scores.argtypes = [vp, vp, i32, vp, vp, i32, i64, vp, vp]
         _lib = lib
@@ -306,6 +312,42 @@ def encode_tokens(tokens: torch.Tensor, centroids: torch.Tensor, cutoffs: torch.
     return codes, res
 
 
+def kmeans_assign(points: torch.Tensor, centroids: torch.Tensor) -> torch.Tensor:
+    """Nearest centroid (squared distance) of every fp16 CUDA point [n, 128]: int32 [n] (fpb_kmeans_assign)."""
+    _require_cuda()
+    lib = load_library()
+    dev = points.device
+    points = points.to(torch.float16).contiguous()
+    centroids = centroids.to(dev, torch.float16).contiguous()
+    bias = (-0.5 * (centroids.float() ** 2).sum(1)).contiguous()
+    out = torch.empty((points.shape[0],), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.fpb_kmeans_assign(dev.index, int(points.shape[1]), int(centroids.shape[0]), centroids.data_ptr(),
+                                     bias.data_ptr(), points.data_ptr(), int(points.shape[0]), out.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+def kmeans_update(points: torch.Tensor, assign: torch.Tensor, centroids: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """In-place mean update of `centroids` (fp16 CUDA [K, 128]) from the assignment; returns (counts int64 [K],
+    shift f32 [K] = |new - old| of the non-empty clusters, 0 elsewhere).  Deterministic: the points of a cluster
+    are summed in index order (fpb_kmeans_update)."""
+    _require_cuda()
+    lib = load_library()
+    dev = points.device
+    K = int(centroids.shape[0])
+    order = torch.argsort(assign.to(torch.int64), stable=True)
+    counts = torch.bincount(assign.to(torch.int64), minlength=K)
+    seg = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+    seg[1:] = counts.cumsum(0)
+    shift = torch.zeros(K, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.fpb_kmeans_update(dev.index, int(points.shape[1]), K, points.data_ptr(), order.data_ptr(),
+                                     seg.data_ptr(), centroids.data_ptr(), shift.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream))
+    return counts, shift
+
+
 def shard_tensors(data: IndexTensors, rank: int, world: int) -> tuple[IndexTensors, int]:
     """Contiguous document-range shard ``rank`` of ``world``.
 
@@ -348,13 +390,20 @@ UPLOAD_DIRECT_BYTES = 256 << 20
 UPLOAD_CHUNK_BYTES = 64 << 20
 
 
-def upload_narrow(src: torch.Tensor, device: torch.device, dtype: torch.dtype) -> torch.Tensor:
-    """src (host, any integer/float dtype, contiguous in dim 0) -> new device tensor of `dtype`."""
+def upload_narrow(src: torch.Tensor, device: torch.device, dtype: torch.dtype,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """src (host, any integer/float dtype, contiguous in dim 0) -> device tensor of `dtype` (`out`, a device tensor
+    of the same shape, or a new one).  `src` may be a view of a memory-mapped .npy file: the staging pass is then
+    also the disk read."""
     src = src if src.is_contiguous() else src.contiguous()
     out_bytes = src.numel() * torch.empty((), dtype=dtype).element_size()
     if src.device.type != "cpu" or out_bytes <= UPLOAD_DIRECT_BYTES or src.dim() == 0 or src.shape[0] == 0:
-        return src.to(device, dtype).contiguous()
-    out = torch.empty(src.shape, dtype=dtype, device=device)
+        if out is None:
+            return src.to(device, dtype).contiguous()
+        out.copy_(src.to(dtype) if src.device.type == "cpu" else src)
+        return out
+    if out is None:
+        out = torch.empty(src.shape, dtype=dtype, device=device)
     row_bytes = max(1, out_bytes // src.shape[0])
     rows = max(1, UPLOAD_CHUNK_BYTES // row_bytes)
     stage = [torch.empty((rows,) + tuple(src.shape[1:]), dtype=dtype).pin_memory() for _ in range(2)]

@@ -52,6 +52,8 @@ def lloyd_kmeans(data: torch.Tensor, k: int, niters: int, seed: int, device: tor
         raise ValueError(f"Number of training points ({n}) is less than k ({k}).")
     dtype = torch.float16 if device.type == "cuda" else torch.float32
     centroids = data[torch.randperm(n)[:k]].to(device=device, dtype=dtype).clone()
+    if device.type == "cuda" and data.shape[1] == 128:
+        return _lloyd_kmeans_b200(data, centroids, niters, n, device)
     data_norms = (data.float() ** 2).sum(1)
     for _ in range(niters):
         cnorm = (centroids**2).sum(1)
@@ -81,6 +83,36 @@ def lloyd_kmeans(data: torch.Tensor, k: int, niters: int, seed: int, device: tor
         shift = torch.norm(new.float() - centroids.float(), dim=1).sum().item()
         centroids = new
         if shift < 1e-8:
+            break
+    return centroids.float().cpu()
+
+
+def _lloyd_kmeans_b200(data: torch.Tensor, centroids: torch.Tensor, niters: int, n: int,
+                       device: torch.device, chunk: int = 4_000_000) -> torch.Tensor:
+    """The same Lloyd iterations on the sm_100a kernels (csrc/encode.cu): the assignment is the tcgen05 argmax
+    GEMM with a -|c|^2/2 bias in the epilogue (fpb_kmeans_assign), the update a deterministic segmented mean
+    (fpb_kmeans_update); empty clusters are re-seeded from random points and the loop stops on a zero shift, as
+    kmeans.py:196-218 does.  The points are staged to the GPU in `chunk`-row pieces when they live on the host."""
+    from ..engine import kmeans_assign, kmeans_update
+
+    on_gpu = data.is_cuda
+    pts = data.to(device=device, dtype=torch.float16) if (on_gpu or n <= chunk) else None
+    for _ in range(niters):
+        if pts is not None:
+            assign = kmeans_assign(pts, centroids)
+            counts, shift = kmeans_update(pts, assign, centroids)
+        else:  # host-resident sample larger than one staging chunk: assign chunk by chunk, one update at the end
+            parts = [kmeans_assign(data[s : s + chunk].to(device=device, dtype=torch.float16), centroids)
+                     for s in range(0, n, chunk)]
+            assign = torch.cat(parts)
+            counts, shift = kmeans_update(data.to(device=device, dtype=torch.float16), assign, centroids)
+        empty = (counts == 0).nonzero(as_tuple=True)[0]
+        moved = float(shift.sum())
+        if len(empty) > 0:
+            old = centroids[empty].float()
+            centroids[empty] = data[torch.randint(0, n, (len(empty),))].to(device=device, dtype=torch.float16)
+            moved += float(torch.norm(centroids[empty].float() - old, dim=1).sum())
+        if moved < 1e-8:
             break
     return centroids.float().cpu()
 

@@ -90,6 +90,73 @@ def read_index(index_path: str) -> IndexTensors | None:
     )
 
 
+def read_index_to_device(index_path: str, device: str | torch.device,
+                         doc_range: tuple[int, int] | None = None) -> tuple[IndexTensors, int] | None:
+    """Loader fast path (replaces load.py:35-322 for a CUDA device): the big arrays go
+    chunk file -> pinned staging -> HBM without ever existing as one host tensor.  Every ``{i}.codes.npy`` /
+    ``{i}.residuals.npy`` is memory-mapped and only the rows of the documents in ``doc_range`` (a shard's
+    contiguous document range; default: all) are read; the int64 codes are narrowed to int32 by the staging pass.
+    A shard's inverted file is rebuilt on the GPU from its own codes (ids local to the shard) instead of filtering
+    the global ``ivf.npy`` on the host.  Returns (tensors with the big arrays on `device`, doc_id_base)."""
+    from ..engine import upload_narrow
+    from .layout import build_ivf
+
+    meta = read_metadata(index_path)
+    if meta is None:
+        return None
+    dev = torch.device(device)
+    num_chunks = int(meta["num_chunks"])
+    nbits = int(meta["nbits"])
+    centroids = torch.from_numpy(_npy(os.path.join(index_path, "centroids.npy"))).to(torch.float16)
+    weights = torch.from_numpy(_npy(os.path.join(index_path, "bucket_weights.npy"))).to(torch.float16)
+    dim = int(centroids.shape[1])
+    pd = dim * nbits // 8
+    chunk_lens: list[list[int]] = []
+    for i in range(num_chunks):
+        p = os.path.join(index_path, f"doclens.{i}.json")
+        if os.path.exists(p):
+            with open(p) as f:
+                chunk_lens.append(json.load(f))
+        else:
+            chunk_lens.append([])
+    all_lens = torch.tensor([x for c in chunk_lens for x in c], dtype=torch.int64)
+    n_docs = int(all_lens.shape[0])
+    lo, hi = (0, n_docs) if doc_range is None else (max(0, int(doc_range[0])), min(n_docs, int(doc_range[1])))
+    offs = torch.zeros(n_docs + 1, dtype=torch.int64)
+    offs[1:] = all_lens.cumsum(0)
+    t0, t1 = int(offs[lo]), int(offs[hi])
+    codes = torch.empty((max(t1 - t0, 0),), dtype=torch.int32, device=dev)
+    residuals = torch.empty((max(t1 - t0, 0), pd), dtype=torch.uint8, device=dev)
+    c0 = 0  # first token of the chunk in the whole index
+    with torch.cuda.device(dev):
+        for i in range(num_chunks):
+            n_tok = int(sum(chunk_lens[i]))
+            a, b = max(c0, t0), min(c0 + n_tok, t1)
+            if a < b:
+                cm = np.load(os.path.join(index_path, f"{i}.codes.npy"), mmap_mode="r")
+                rm = np.load(os.path.join(index_path, f"{i}.residuals.npy"), mmap_mode="r")
+                upload_narrow(torch.from_numpy(cm[a - c0 : b - c0]), dev, torch.int32, out=codes[a - t0 : b - t0])
+                upload_narrow(torch.from_numpy(rm[a - c0 : b - c0]), dev, torch.uint8, out=residuals[a - t0 : b - t0])
+                del cm, rm
+            c0 += n_tok
+        ivf = ivf_lengths = None
+        ivf_p = os.path.join(index_path, "ivf.npy")
+        ivfl_p = os.path.join(index_path, "ivf_lengths.npy")
+        if os.path.exists(ivf_p) and os.path.exists(ivfl_p):  # absent => compress_only
+            if lo == 0 and hi == n_docs:
+                ivf = upload_narrow(torch.from_numpy(np.load(ivf_p, mmap_mode="r")), dev, torch.int32)
+                ivf_lengths = torch.from_numpy(np.load(ivfl_p)).to(torch.int32)
+            else:
+                n_cells = max(int(centroids.shape[0]), int(meta.get("num_partitions", 0)))
+                ivf64, ivf_lengths = build_ivf(codes, all_lens[lo:hi], n_cells)
+                ivf = ivf64.to(torch.int32)
+                del ivf64
+        torch.cuda.synchronize(dev)
+    data = IndexTensors(nbits=nbits, centroids=centroids, bucket_weights=weights, doc_lengths=all_lens[lo:hi],
+                        doc_codes=codes, doc_residuals=residuals, ivf=ivf, ivf_lengths=ivf_lengths)
+    return data, lo
+
+
 def write_codec(index_path: str, centroids: torch.Tensor, cutoffs: torch.Tensor, weights: torch.Tensor,
                 avg_residual: torch.Tensor, cluster_threshold: torch.Tensor) -> None:
     """create.rs:333-339, :380-397 (dtypes: centroids f16, the rest f32)."""

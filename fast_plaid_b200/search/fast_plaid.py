@@ -157,6 +157,22 @@ class FastPlaid:
         new: dict[str, DeviceIndex | None] = {d: None for d in self.devices}
         if not os.path.exists(os.path.join(self.index, "metadata.json")):
             return new
+        if len(self.devices) == 1 and self.devices[0] != "cpu":
+            # loader fast path: chunk files -> pinned staging -> HBM, only this shard's document range
+            dev = self.devices[0]
+            try:
+                n_docs = read_num_documents(self.index)
+                rng = None
+                if self.shard is not None:
+                    _, doc_shard, n_shards = _engine.shard_grid(self.shard[0], self.shard[1], self.query_groups)
+                    rng = ((n_docs * doc_shard) // n_shards, (n_docs * (doc_shard + 1)) // n_shards)
+                loaded = _store.read_index_to_device(self.index, dev, rng)
+                if loaded is not None:
+                    new[dev] = DeviceIndex(loaded[0], dev, doc_id_base=loaded[1])
+            except Exception as e:  # load.py:393-399, :414-416
+                print(f"Warning: Failed to load index on {dev}: {e}")
+            self._host_data = None
+            return new
         try:
             data = _store.read_index(self.index)
         except Exception as e:  # load.py:393-399

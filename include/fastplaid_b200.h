@@ -307,6 +307,19 @@ int fpb_encode(int device, int nbits, int dim, int64_t n_centroids, const void* 
                const void* d_tokens, int64_t n_tokens, const float* d_cutoffs, int32_t* d_codes,
                uint8_t* d_residuals, void* stream);
 
+/* ---- index build: Lloyd iterations of the centroid k-means (python/fast_plaid/search/kmeans.py:60-223) ----
+ * fpb_kmeans_assign : assign[i] = argmax_k (<x_i, c_k> + bias[k]) in fp32 on the tensor cores; with
+ *                     bias[k] = -|c_k|^2 / 2 that is the nearest centroid by squared distance (kmeans.py:153-160);
+ *                     ties -> smallest k.   d_points f16 [n, 128], d_centroids f16 [K, 128], d_bias f32 [K]
+ * fpb_kmeans_update : centroid k <- mean of its points, as a deterministic segmented sum: d_order i64 [n] = point
+ *                     indices sorted by assignment, d_seg_offsets i64 [K+1]; empty segments are left untouched
+ *                     (the caller re-seeds them, kmeans.py:196-205); d_shift f32 [K] (optional) receives
+ *                     |new - old| per centroid for the convergence test */
+int fpb_kmeans_assign(int device, int dim, int64_t n_centroids, const void* d_centroids, const float* d_bias,
+                      const void* d_points, int64_t n_points, int32_t* d_assign, void* stream);
+int fpb_kmeans_update(int device, int dim, int64_t n_centroids, const void* d_points, const int64_t* d_order,
+                      const int64_t* d_seg_offsets, void* d_centroids, float* d_shift, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
