@@ -46,12 +46,12 @@ def lloyd_kmeans(data: torch.Tensor, k: int, niters: int, seed: int, device: tor
     torch.manual_seed(seed)  # kmeans.py:236-238
     n = data.shape[0]
     if max_points_per_centroid is not None and n > k * max_points_per_centroid:
-        data = data[torch.randperm(n)[: k * max_points_per_centroid]]
+        data = data[torch.randperm(n)[: k * max_points_per_centroid].to(data.device)]
         n = data.shape[0]
     if n < k:
         raise ValueError(f"Number of training points ({n}) is less than k ({k}).")
     dtype = torch.float16 if device.type == "cuda" else torch.float32
-    centroids = data[torch.randperm(n)[:k]].to(device=device, dtype=dtype).clone()
+    centroids = data[torch.randperm(n)[:k].to(data.device)].to(device=device, dtype=dtype).clone()
     if device.type == "cuda" and data.shape[1] == 128:
         return _lloyd_kmeans_b200(data, centroids, niters, n, device)
     data_norms = (data.float() ** 2).sum(1)
@@ -110,7 +110,7 @@ def _lloyd_kmeans_b200(data: torch.Tensor, centroids: torch.Tensor, niters: int,
         moved = float(shift.sum())
         if len(empty) > 0:
             old = centroids[empty].float()
-            centroids[empty] = data[torch.randint(0, n, (len(empty),))].to(device=device, dtype=torch.float16)
+            centroids[empty] = data[torch.randint(0, n, (len(empty),)).to(data.device)].to(device=device, dtype=torch.float16)
             moved += float(torch.norm(centroids[empty].float() - old, dim=1).sum())
         if moved < 1e-8:
             break
@@ -128,16 +128,21 @@ def compute_kmeans(documents_embeddings: list[torch.Tensor] | torch.Tensor, dim:
         n_samples_kmeans = min(1 + int(16 * math.sqrt(120 * n_docs)), n_docs)
     n_samples_kmeans = min(n_docs, n_samples_kmeans)
     idx = torch.randperm(n_docs)[:n_samples_kmeans]
+    dev = torch.device(device)
     if isinstance(documents_embeddings, torch.Tensor):
         samples = documents_embeddings[idx].reshape(-1, dim)
     else:
-        samples = torch.cat([documents_embeddings[i].reshape(-1, dim).to("cpu", torch.float16) for i in idx.tolist()])
+        # the sampled documents stay where they live: on the host for host documents, in HBM for CUDA documents
+        # (visited in ascending order so that a lazy, block-generated corpus produces each block once)
+        order = sorted(idx.tolist())
+        first = documents_embeddings[order[0]]
+        keep = first.device if first.is_cuda else torch.device("cpu")
+        samples = torch.cat([documents_embeddings[i].reshape(-1, dim).to(keep, torch.float16) for i in order])
     total = samples.shape[0]
     if num_partitions is None:
         num_partitions = num_partitions_for(total / n_samples_kmeans * n_docs)
     k = min(num_partitions, total)
-    dev = torch.device(device)
-    cent = lloyd_kmeans(samples.cpu(), k, kmeans_niters, seed, dev, max_points_per_centroid)
+    cent = lloyd_kmeans(samples, k, kmeans_niters, seed, dev, max_points_per_centroid)
     return torch.nn.functional.normalize(cent.to(dev), dim=-1).half()
 
 
@@ -169,7 +174,8 @@ def train_codec(docs: list[torch.Tensor], centroids: torch.Tensor, nbits: int, s
     if seed is not None:
         g.manual_seed(int(seed))
     sample_pids = torch.randperm(n_docs, generator=g)[:sample_count].tolist()
-    total = sum(int(docs[p].shape[0]) for p in sample_pids)
+    known = getattr(docs, "doc_lengths", None)
+    total = sum(int(known[p]) if known is not None else int(docs[p].shape[0]) for p in sample_pids)
     heldout_size = int(round(min(0.05 * total, 50_000.0)))
     parts: list[torch.Tensor] = []
     have = 0
@@ -226,7 +232,8 @@ def create_index(docs: list[torch.Tensor], index_path: str, centroids: torch.Ten
     os.makedirs(index_path, exist_ok=True)
     docs_per_chunk = int(min(batch_size, 1 + n_docs))  # create.rs:400
     n_chunks = int(math.ceil(n_docs / min(float(batch_size), 1.0 + n_docs)))  # create.rs:218
-    total_tokens = sum(int(d.shape[0]) for d in docs)
+    known = getattr(docs, "doc_lengths", None)  # a lazy document sequence knows its lengths without generating data
+    total_tokens = int(known.sum()) if known is not None else sum(int(d.shape[0]) for d in docs)
     est_k = num_partitions_for(float(total_tokens))  # create.rs:292-294
     store.write_plan(index_path, nbits, n_chunks)
     codec = train_codec(docs, centroids, nbits, seed, dev)
@@ -238,13 +245,16 @@ def create_index(docs: list[torch.Tensor], index_path: str, centroids: torch.Ten
     all_codes: list[torch.Tensor] = []
     all_lens: list[int] = []
     emb_offset = 0
+    # streaming: one chunk of `docs_per_chunk` documents is resident at a time (the documents may be a lazy sequence)
     for ci in range(n_chunks):
-        chunk_docs = docs[ci * docs_per_chunk : (ci + 1) * docs_per_chunk]
-        lens = [int(d.shape[0]) for d in chunk_docs]
+        d_lo, d_hi = ci * docs_per_chunk, min(n_docs, (ci + 1) * docs_per_chunk)
+        lens: list[int] = []
         codes_parts, res_parts = [], []
         acc: list[torch.Tensor] = []
         rows = 0
-        for d in chunk_docs:
+        for di in range(d_lo, d_hi):
+            d = docs[di]
+            lens.append(int(d.shape[0]))
             acc.append(d.reshape(-1, dim).to(torch.float16))
             rows += int(d.shape[0])
             if rows >= batch_size:

@@ -137,3 +137,49 @@ def synthetic_index(*args, **kwargs):
     return IndexTensors(nbits=a.nbits, centroids=a.centroids, bucket_weights=a.bucket_weights,
                         doc_lengths=a.doc_lengths, doc_codes=a.doc_codes, doc_residuals=a.doc_residuals,
                         ivf=a.ivf, ivf_lengths=a.ivf_lengths), base
+
+
+class SyntheticDocuments:
+    """A lazy, seeded corpus: `len()` documents of `doc_len` L2-normalised random tokens,
+    generated on `device` in blocks of `block` documents when they are asked for, so that FastPlaid.create() can
+    build an index whose raw embeddings (77 GB at 1M x 300 x 128 fp16) never exist at once.  It behaves like the
+    `list[torch.Tensor]` the reference takes: `docs[i]`, `docs[a:b]`, iteration, `len(docs)`; `doc_lengths` lets
+    the builder size things without touching the data."""
+
+    def __init__(self, n_docs: int, doc_len: int, dim: int = 128, seed: int = 7, device: str = "cuda:0",
+                 block: int = 2048, ragged: bool = False) -> None:
+        self.n_docs, self.doc_len, self.dim, self.seed = int(n_docs), int(doc_len), int(dim), int(seed)
+        self.device = torch.device(device)
+        self.block = int(block)
+        if ragged:
+            g = torch.Generator().manual_seed(seed + 1)
+            self.doc_lengths = torch.randint(max(1, doc_len // 4), doc_len + 1, (n_docs,), generator=g)
+        else:
+            self.doc_lengths = torch.full((n_docs,), doc_len, dtype=torch.int64)
+        self._cache: tuple[int, torch.Tensor] | None = None
+
+    def __len__(self) -> int:
+        return self.n_docs
+
+    def _block(self, bi: int) -> torch.Tensor:
+        if self._cache is not None and self._cache[0] == bi:
+            return self._cache[1]
+        g = torch.Generator(device=self.device)
+        g.manual_seed(self.seed * 1_000_003 + bi)
+        x = torch.randn(self.block, self.doc_len, self.dim, generator=g, device=self.device)
+        x = torch.nn.functional.normalize(x, dim=-1).half()
+        self._cache = (bi, x)
+        return x
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self.n_docs))]
+        if i < 0:
+            i += self.n_docs
+        if not 0 <= i < self.n_docs:
+            raise IndexError(i)
+        return self._block(i // self.block)[i % self.block, : int(self.doc_lengths[i])]
+
+    def __iter__(self):
+        for i in range(self.n_docs):
+            yield self[i]

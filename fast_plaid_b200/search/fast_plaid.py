@@ -287,6 +287,8 @@ class FastPlaid:
     def _format_embeddings(self, embeddings):
         if isinstance(embeddings, torch.Tensor):
             return embeddings.squeeze(0) if embeddings.dim() == 3 and embeddings.shape[0] == 1 else embeddings
+        if not isinstance(embeddings, (list, tuple)) and hasattr(embeddings, "__getitem__") and hasattr(embeddings, "__len__"):
+            return embeddings  # a lazy document sequence (e.g. index.synthetic.SyntheticDocuments): never materialised
         return [e.squeeze(0) if e.dim() == 3 else e for e in embeddings]
 
     @staticmethod
@@ -334,7 +336,7 @@ class FastPlaid:
 
                 _meta_create(index=self.index, metadata=metadata)
             if num_docs <= start_from_scratch:
-                save_list_tensors_on_disk(os.path.join(self.index, "embeddings.npy"), docs)
+                save_list_tensors_on_disk(os.path.join(self.index, "embeddings.npy"), [docs[i] for i in range(num_docs)])
             dim = int(docs[0].shape[-1])
             _engine.check_supported(dim, nbits)  # fail before writing an index the engine cannot search
             primary = self.devices[0]

@@ -117,3 +117,71 @@ def test_sharded_equals_unsharded_at_size(big, cuda_device):
     i2, s2, c2 = didx.merge_records(recs, TOP_K)
     torch.cuda.synchronize()
     assert torch.equal(i2, ids) and torch.equal(s2, scores) and torch.equal(c2, counts)
+
+
+def test_cfg2_built_by_create_searches_like_the_oracle(tmp_path, cuda_device):
+    """BASELINE config 2 end to end through the public surface: 100k documents x 300 tokens built by
+    FastPlaid.create() on the GPU (k-means on the sm_100a assign/update kernels, streaming chunk encode, K = 65536),
+    loaded by the direct-to-device loader, searched with B = 64, Q = 32, top_k = 100.  For 8 queries every integer
+    stage must equal the canonical oracle given the GPU's own S -- probed cells, candidates, approximate scores
+    (or the pruned list from the GPU's approximate scores when a fp32 sum rounds differently), pruned list -- and
+    the returned ranking must be a 1e-3-valid ranking of the oracle's exact scores."""
+    import time
+
+    from fast_plaid_b200 import search
+    from fast_plaid_b200.engine import FPB_FLAG_APPROX_EXACT_ALL, DeviceIndex
+    from fast_plaid_b200.index import store
+    from fast_plaid_b200.index.synthetic import SyntheticDocuments
+
+    n_docs, doc_len, B, Q, top_k = 100_000, 300, 64, 32, 100
+    docs = SyntheticDocuments(n_docs, doc_len, device=cuda_device, seed=11)
+    path = str(tmp_path / "cfg2")
+    fp = search.FastPlaid(path, device=cuda_device)
+    t0 = time.time()
+    fp.create(docs, kmeans_niters=4, seed=42)
+    t_create = time.time() - t0
+    meta = store.read_metadata(path)
+    assert meta["num_documents"] == n_docs and meta["num_embeddings"] == n_docs * doc_len
+    assert meta["num_partitions"] == 65536
+    # queries: noisy copies of document tokens
+    g = torch.Generator().manual_seed(5)
+    src = torch.randint(0, n_docs, (B,), generator=g).tolist()
+    queries = torch.stack([torch.nn.functional.normalize(
+        docs[d].float().cpu()[torch.randint(0, doc_len, (Q,), generator=g)] + 0.2 * torch.randn(Q, 128, generator=g), dim=-1)
+        for d in sorted(src)])
+    t0 = time.time()
+    res = fp.search(queries, top_k=top_k)
+    t_search = time.time() - t0
+    assert len(res) == B and all(len(r) == top_k for r in res)
+    print(f"[cfg2] create() {t_create:.1f} s, first search of 64 queries {t_search * 1e3:.1f} ms")
+    # the source document is found (tests/test.py relevance idea: queries are copies of its tokens)
+    hits = sum(int(d == r[0][0]) for d, r in zip(sorted(src), res))
+    assert hits >= B // 2, hits
+    # oracle on the directory the builder wrote
+    data = store.read_index(path)
+    oidx = po.OracleIndex(data.nbits, data.centroids, data.bucket_weights, data.ivf, data.ivf_lengths.long(),
+                          data.doc_codes, data.doc_residuals, data.doc_lengths)
+    didx = fp.indices[cuda_device]
+    params = DeviceIndex.make_params(top_k, 4096, 8)
+    nq = 8
+    st = didx.run_stages(queries[:nq].half().to(cuda_device), DeviceIndex.with_flags(params, FPB_FLAG_APPROX_EXACT_ALL))
+    torch.cuda.synchronize()
+    for b in range(nq):
+        S_b = st["S"][b, :, :Q].cpu().contiguous()
+        ref = po.search_one(queries[b], oidx, 8, 2000, 4096, top_k, ties="canonical", return_stages=True, inject={"S": S_b})
+        cells = torch.unique(st["cells"][b].cpu().flatten().long())
+        assert torch.equal(cells[cells >= 0], ref["cells"]), f"query {b}: probed cells differ"
+        n = int(st["n_cand"][b])
+        assert n > 30_000
+        assert torch.equal(st["cand"][b, :n].cpu().long(), ref["candidates"]), f"query {b}: candidates differ"
+        approx = st["approx"][b, :n].cpu()
+        if not torch.equal(approx, ref["approx"]):
+            assert float(((approx - ref["approx"]).abs() / ref["approx"].abs().clamp_min(1.0)).max()) < 1e-6
+            ref = po.search_one(queries[b], oidx, 8, 2000, 4096, top_k, ties="canonical", return_stages=True,
+                                inject={"S": S_b, "approx": approx})
+        r = int(st["n_rerank"][b])
+        assert torch.equal(st["rerank"][b, :r].cpu().long(), ref["rerank"]), f"query {b}: pruned list differs"
+        ok, why = ranking_consistent([d for d, _ in res[b]], [s for _, s in res[b]],
+                                     dict(zip(ref["rerank"].tolist(), ref["exact"].tolist())), 1e-3)
+        assert ok, f"query {b}: {why}"
+    fp.close()
