@@ -25,6 +25,10 @@ struct fpb_index {
   const int64_t* doc_offsets;
   const int32_t* doc_codes;
   const uint8_t* doc_residuals;
+  // derived at load time: fp16 norm of every decompressed token, n_t = fp16(sqrt(sum_fp32 e^2)) (search.rs:86-93).
+  // It is a property of the token, not of the (query, document) pair: the MaxSim kernels read it (2 B/token)
+  // instead of re-deriving it for every pair.  Caller-owned buffer filled by fpb_index_create.
+  const __half* token_norms;
   const int64_t* ivf_offsets;  // nullptr => compress_only
   const int32_t* ivf_pids;
   // w_perm[i] = bucket_weights[bitrev_nbits(i)]  (closed form of the two LUTs of

@@ -5,7 +5,7 @@
 
 #include <cuda.h>
 
-#include "common.cuh"
+#include "kernels.h"
 
 // The driver-API entry point is resolved at run time (no link against libcuda).
 typedef CUresult (*fpb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -47,7 +47,7 @@ void fpb_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* fpb_last_error(void) { return g_err; }
-extern "C" int fpb_abi_version(void) { return 5; }  // 5: two-pass approximate stage (layout fields, FPB_FLAG_APPROX_*), fpb_comm_* + fpb_search_batch_sharded
+extern "C" int fpb_abi_version(void) { return 6; }  // 6: d_token_norms of fpb_index_create; 5: two-pass approximate stage (layout fields, FPB_FLAG_APPROX_*), fpb_comm_* + fpb_search_batch_sharded
 
 static int bitrev(int x, int nbits) {
   int r = 0;
@@ -59,7 +59,7 @@ static int bitrev(int x, int nbits) {
 extern "C" int fpb_index_create(fpb_index** out, int device, int nbits, int dim, int64_t n_centroids,
                                 const void* d_centroids, const void* d_bucket_weights,
                                 int64_t n_docs, const int64_t* d_doc_offsets,
-                                const int32_t* d_doc_codes, const uint8_t* d_doc_residuals,
+                                const int32_t* d_doc_codes, const uint8_t* d_doc_residuals, void* d_token_norms,
                                 const int64_t* d_ivf_offsets, const int32_t* d_ivf_pids,
                                 int64_t n_ivf, int64_t max_doc_len, int64_t doc_id_base) {
   if (!out) {
@@ -100,6 +100,7 @@ extern "C" int fpb_index_create(fpb_index** out, int device, int nbits, int dim,
   ix->doc_offsets = d_doc_offsets;
   ix->doc_codes = d_doc_codes;
   ix->doc_residuals = d_doc_residuals;
+  ix->token_norms = static_cast<const __half*>(d_token_norms);
   ix->ivf_offsets = d_ivf_offsets;
   ix->ivf_pids = d_ivf_pids;
   cudaDeviceProp prop;
@@ -129,6 +130,20 @@ extern "C" int fpb_index_create(fpb_index** out, int device, int nbits, int dim,
     }
   }
   ix->E = n_tokens;
+  if (n_tokens > 0 && !d_token_norms) {
+    delete ix;
+    fpb_set_error("fpb_index_create: d_token_norms (f16 [n_tokens], filled here) is NULL");
+    return FPB_ERR_INVALID;
+  }
+  if (n_tokens > 0) {  // derive the per-token norms once (default stream, synchronous: creation is not a hot path)
+    const int rc = launch_token_norms(ix, static_cast<__half*>(d_token_norms), nullptr);
+    e = rc == FPB_OK ? cudaDeviceSynchronize() : cudaSuccess;
+    if (rc != FPB_OK || e != cudaSuccess) {
+      delete ix;
+      if (rc == FPB_OK) fpb_set_error("token norm kernel failed: %s", cudaGetErrorString(e));
+      return rc != FPB_OK ? rc : FPB_ERR_CUDA;
+    }
+  }
   make_centroid_tmap(ix);
   *out = ix;
   return FPB_OK;

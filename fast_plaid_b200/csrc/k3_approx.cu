@@ -82,10 +82,16 @@ __device__ __forceinline__ void k3_reduce_groups(__half2& m0, __half2& m1, __hal
     m3 = __hmax2(m3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(m3), off)));
   }
 }
-template <int LPR>
+template <int LPR, bool FULLQ = false>
 __device__ __forceinline__ float k3_sum_columns(__half2 m0, __half2 m1, __half2 m2, __half2 m3, int col0, int Q) {
   float s = 0.f;
   const float2 f0 = __half22float2(m0), f1 = __half22float2(m1), f2 = __half22float2(m2), f3 = __half22float2(m3);
+  if constexpr (FULLQ) {  // Q == Qp: every column is a real query token; same additions in the same order
+    s += f0.x; s += f0.y; s += f1.x; s += f1.y; s += f2.x; s += f2.y; s += f3.x; s += f3.y;
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    return s;
+  }
   if (col0 + 0 < Q) s += f0.x;
   if (col0 + 1 < Q) s += f0.y;
   if (col0 + 2 < Q) s += f1.x;
@@ -407,7 +413,7 @@ __device__ __forceinline__ void k3_sts_if(uint32_t addr, uint32_t v, uint32_t pr
   asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
 }
 
-template <int LPR, int MINB, int W, int U>
+template <int LPR, int MINB, int W, int U, bool FULLQ>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
                 const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
@@ -462,6 +468,8 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
     __syncthreads();
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP) + sub;
     const uint4* tqp = reinterpret_cast<const uint4*>(tau + int64_t(b) * QP + sub * 8);
+    float* ub_chunk = ub_out + int64_t(b) * cand_cap + int64_t(s_c) * K3A_DOCS_PER_CHUNK;
+    float* lb_chunk = lb_out + int64_t(b) * cand_cap + int64_t(s_c) * K3A_DOCS_PER_CHUNK;
 
     // ---- the warp's documents are slots warp*DPW .. warp*DPW + DPW - 1 of the chunk, walked group by group ----
     int slot = warp * DPW;
@@ -566,26 +574,19 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
         rows += tail;
         toks += unsigned(len);
         k3_reduce_groups<LPR>(m0, m1, m2, m3);
-        // lower bound: the maxima over the gathered rows; upper bound: unresolved columns raised to tau
+        // lower bound: the maxima over the gathered rows; upper bound: unresolved columns raised to tau.  Both sums
+        // use the exact kernel's order, fp32 addition is monotone, so lb <= approx <= ub; when no column was raised
+        // the two are the same additions of the same values, and whenever lb == ub the score is pinned between them:
+        // "resolved" needs no flag, it IS lb == ub.
         const uint4 tq = __ldg(tqp);
-        const __half2 t0 = u32_as_half2(tq.x), t1 = u32_as_half2(tq.y), t2 = u32_as_half2(tq.z), t3 = u32_as_half2(tq.w);
         const int col0 = sub * 8;
-        const float lb = k3_sum_columns<LPR>(m0, m1, m2, m3, col0, Q);
-        const float ub = k3_sum_columns<LPR>(__hmax2(m0, t0), __hmax2(m1, t1), __hmax2(m2, t2), __hmax2(m3, t3), col0, Q);
-        // a column is unresolved when its maximum over the gathered rows is below tau (padded columns: tau = +inf,
-        // but they are outside the sums and must not count)
-        const unsigned l0 = __hlt2_mask(m0, t0) & ((col0 + 0 < Q ? 0xffffu : 0u) | (col0 + 1 < Q ? 0xffff0000u : 0u));
-        const unsigned l1 = __hlt2_mask(m1, t1) & ((col0 + 2 < Q ? 0xffffu : 0u) | (col0 + 3 < Q ? 0xffff0000u : 0u));
-        const unsigned l2 = __hlt2_mask(m2, t2) & ((col0 + 4 < Q ? 0xffffu : 0u) | (col0 + 5 < Q ? 0xffff0000u : 0u));
-        const unsigned l3 = __hlt2_mask(m3, t3) & ((col0 + 6 < Q ? 0xffffu : 0u) | (col0 + 7 < Q ? 0xffff0000u : 0u));
-        const bool unres = __any_sync(0xffffffffu, (l0 | l1 | l2 | l3) != 0u);
+        const float lb = k3_sum_columns<LPR, FULLQ>(m0, m1, m2, m3, col0, Q);
+        const float ub = k3_sum_columns<LPR, FULLQ>(__hmax2(m0, u32_as_half2(tq.x)), __hmax2(m1, u32_as_half2(tq.y)),
+                                                    __hmax2(m2, u32_as_half2(tq.z)), __hmax2(m3, u32_as_half2(tq.w)),
+                                                    col0, Q);
         if (lane == 0) {
-          const int64_t at = int64_t(b) * cand_cap + (s_c * K3A_DOCS_PER_CHUNK + slot);
-          float l = lb;
-          if (!unres) l = ub;                                       // resolved: ub is the exact score
-          else if (!(l < ub)) l = ub - fabsf(ub) * 1e-6f - 1e-30f;  // keep "unresolved" visible as lb < ub
-          ub_out[at] = ub;
-          lb_out[at] = l;
+          ub_chunk[slot] = ub;
+          lb_chunk[slot] = lb;
         }
         if (nlen < 0) break;  // no further document for this warp in the chunk
         head = tail = 0;
@@ -1118,13 +1119,15 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
                  int32_t*, int, const __half*, const uint32_t*, int, float*, float*, unsigned long long*);
     int minb, wq;
     constexpr int TPI = 32 / LPR;
+    const bool fullq = L.Q == L.Qp;
+#define K3_BOUND(MB, WW, UU) (fullq ? k3_bound_kernel<LPR, MB, WW, UU, true> : k3_bound_kernel<LPR, MB, WW, UU, false>)
     switch (shape) {
-      case 1: kern = k3_bound_kernel<LPR, 5, 4, 4>; minb = 5; wq = K3_WQ_FOR(4, 4 * TPI); break;
-      case 2: kern = k3_bound_kernel<LPR, 4, 12, 4>; minb = 4; wq = K3_WQ_FOR(12, 4 * TPI); break;
-      case 3: kern = k3_bound_kernel<LPR, 4, 8, 4>; minb = 4; wq = K3_WQ_FOR(8, 4 * TPI); break;
-      case 4: kern = k3_bound_kernel<LPR, 5, 6, 4>; minb = 5; wq = K3_WQ_FOR(6, 4 * TPI); break;
-      default: kern = k3_bound_kernel<LPR, 4, 6, 4>; minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
+      case 1: kern = K3_BOUND(5, 4, 4); minb = 5; wq = K3_WQ_FOR(4, 4 * TPI); break;
+      case 2: kern = K3_BOUND(4, 12, 4); minb = 4; wq = K3_WQ_FOR(12, 4 * TPI); break;
+      case 3: kern = K3_BOUND(4, 11, 4); minb = 4; wq = K3_WQ_FOR(11, 4 * TPI); break;
+      default: kern = K3_BOUND(4, 6, 4); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
     }
+#undef K3_BOUND
     const size_t smem = size_t(L.hb_words + 4) * 4 + size_t(K3_THREADS / 32) * wq * 4;
     FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)

@@ -96,17 +96,11 @@ __device__ __forceinline__ float div_rn(float e, float n, float r) {
 
 // Decompress + normalise one token slice (the lane's 16 residual bytes) into `dst`
 // (shared or global), returning nothing.  LPT lanes cooperate on one token.
-template <int D, int NBITS, int LPT>
-__device__ __forceinline__ void decompress_slice(const uint32_t* lut, const uint8_t* __restrict__ residuals,
-                                                 const __half* __restrict__ C, int64_t tok_global, int code,
-                                                 int sub, __half* dst_row) {
-  constexpr int PD = D * NBITS / 8;
-  constexpr int EPL = D / LPT;  // elements per lane
-  constexpr int NH2 = EPL / 2;
-  const uint4 rv = ldg_nc_na(reinterpret_cast<const uint4*>(residuals + tok_global * PD) + sub);
-  const uint4* cent = reinterpret_cast<const uint4*>(C + int64_t(code) * D + sub * EPL);
-  __half2 e[NH2];
-  Decoder<NBITS>::decode16(lut, rv, cent, e);
+// fp16 norm of the token whose slice `e` this lane holds: fp32 sum of squares (per lane in element order, then over
+// the LPT lanes of the token), square root, one rounding to fp16 (norm(...).half(), search.rs:86-93; the
+// clamp_min(1e-12) that follows is a no-op in fp16).  THE definition of the per-token norm table.
+template <int NH2, int LPT>
+__device__ __forceinline__ __half slice_norm(const __half2 (&e)[NH2]) {
   float ss = 0.f;
 #pragma unroll
   for (int p = 0; p < NH2; ++p) {
@@ -116,7 +110,21 @@ __device__ __forceinline__ void decompress_slice(const uint32_t* lut, const uint
   }
 #pragma unroll
   for (int off = 1; off < LPT; off <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-  const float nf = __half2float(__float2half_rn(sqrtf(ss)));  // norm(...).half(); clamp_min(1e-12) is a no-op in fp16
+  return __float2half_rn(sqrtf(ss));
+}
+
+template <int D, int NBITS, int LPT>
+__device__ __forceinline__ void decompress_slice(const uint32_t* lut, const uint8_t* __restrict__ residuals,
+                                                 const __half* __restrict__ C, const __half* __restrict__ norms,
+                                                 int64_t tok_global, int code, int sub, __half* dst_row) {
+  constexpr int PD = D * NBITS / 8;
+  constexpr int EPL = D / LPT;  // elements per lane
+  constexpr int NH2 = EPL / 2;
+  const uint4 rv = ldg_nc_na(reinterpret_cast<const uint4*>(residuals + tok_global * PD) + sub);
+  const uint4* cent = reinterpret_cast<const uint4*>(C + int64_t(code) * D + sub * EPL);
+  __half2 e[NH2];
+  Decoder<NBITS>::decode16(lut, rv, cent, e);
+  const float nf = __half2float(norms[tok_global]);  // derived once per token at index load (k5_token_norms_kernel)
   const float r = __frcp_rn(nf);
   uint32_t out[NH2];
 #pragma unroll
@@ -132,7 +140,8 @@ __device__ __forceinline__ void decompress_slice(const uint32_t* lut, const uint
 template <int D, int NBITS, int QP>
 __global__ void __launch_bounds__(K5_THREADS)
 k5_maxsim_kernel(const __half* __restrict__ C, const int64_t* __restrict__ doc_offsets,
-                 const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals, WPerm wp,
+                 const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals,
+                 const __half* __restrict__ norms, WPerm wp,
                  const __half* __restrict__ Qpad, int Q, int B, int R, const int32_t* __restrict__ n_rerank,
                  const int32_t* __restrict__ rerank, float* __restrict__ exact) {
   constexpr int LDS = K5Smem<D, QP>::LDS;
@@ -179,7 +188,7 @@ k5_maxsim_kernel(const __half* __restrict__ C, const int64_t* __restrict__ doc_o
       for (int tok = tid / LPT; tok < K5_TILE; tok += K5_THREADS / LPT) {
         const int tt = min(tile0 + tok, len - 1);
         const int code = __ldg(codes + o0 + tt);
-        decompress_slice<D, NBITS, LPT>(lut, residuals, C, o0 + tt, code, tid % LPT, As + tok * LDS);
+        decompress_slice<D, NBITS, LPT>(lut, residuals, C, norms, o0 + tt, code, tid % LPT, As + tok * LDS);
       }
       __syncthreads();
       // ---- ts = A(64 x D) . Q^T, 16 rows per warp ----
@@ -244,7 +253,8 @@ k5_maxsim_kernel(const __half* __restrict__ C, const int64_t* __restrict__ doc_o
 template <int D, int NBITS>
 __global__ void __launch_bounds__(K5_THREADS)
 k5_reconstruct_kernel(const __half* __restrict__ C, const int64_t* __restrict__ doc_offsets,
-                      const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals, WPerm wp,
+                      const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals,
+                      const __half* __restrict__ norms, WPerm wp,
                       const int32_t* __restrict__ doc_ids, int n, const int64_t* __restrict__ out_offsets,
                       __half* __restrict__ out) {
   constexpr int PD = D * NBITS / 8;
@@ -263,7 +273,7 @@ k5_reconstruct_kernel(const __half* __restrict__ C, const int64_t* __restrict__ 
       if (len > 0) {
         const int code = __ldg(codes + o0 + tt);
         // duplicate writes of the last row by the padding groups store identical bytes
-        decompress_slice<D, NBITS, LPT>(lut, residuals, C, o0 + tt, code, threadIdx.x % LPT, out + (oo + tt) * D);
+        decompress_slice<D, NBITS, LPT>(lut, residuals, C, norms, o0 + tt, code, threadIdx.x % LPT, out + (oo + tt) * D);
       }
     }
   }
@@ -273,7 +283,8 @@ k5_reconstruct_kernel(const __half* __restrict__ C, const int64_t* __restrict__ 
 template <int D, int NBITS>
 __global__ void __launch_bounds__(K5_THREADS)
 k5_token_scores_kernel(const __half* __restrict__ C, const int64_t* __restrict__ doc_offsets,
-                       const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals, WPerm wp,
+                       const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals,
+                       const __half* __restrict__ norms, WPerm wp,
                        const __half* __restrict__ queries, int Q, const int32_t* __restrict__ query_of,
                        const int32_t* __restrict__ doc_ids, int n, int64_t max_len, __half* __restrict__ out) {
   // Simple CUDA-core formulation (this is an off-metric by-product): one token per LPT lanes,
@@ -297,7 +308,7 @@ k5_token_scores_kernel(const __half* __restrict__ C, const int64_t* __restrict__
     for (int tok = grp; tok < len_up; tok += step) {
       const int tt = min(tok, len - 1);
       const int code = __ldg(codes + o0 + tt);
-      decompress_slice<D, NBITS, LPT>(lut, residuals, C, o0 + tt, code, sub, &row[grp][0]);
+      decompress_slice<D, NBITS, LPT>(lut, residuals, C, norms, o0 + tt, code, sub, &row[grp][0]);
       __syncwarp();
       if (tok < len) {
         for (int q = sub; q < Q; q += LPT) {
@@ -312,6 +323,32 @@ k5_token_scores_kernel(const __half* __restrict__ C, const int64_t* __restrict__
   }
 }
 
+// The per-token norm table (fpb_index_create): one token per LPT lanes, same decode as everywhere else.
+template <int D, int NBITS>
+__global__ void __launch_bounds__(K5_THREADS)
+k5_token_norms_kernel(const __half* __restrict__ C, const int32_t* __restrict__ codes,
+                      const uint8_t* __restrict__ residuals, WPerm wp, int64_t n_tokens, __half* __restrict__ out) {
+  constexpr int PD = D * NBITS / 8;
+  constexpr int LPT = PD / 16;
+  constexpr int EPL = D / LPT;
+  constexpr int NH2 = EPL / 2;
+  __shared__ uint32_t lut[512];
+  Decoder<NBITS>::build(lut, wp, threadIdx.x, K5_THREADS);
+  __syncthreads();
+  const int sub = threadIdx.x % LPT;
+  const int64_t per_cta = K5_THREADS / LPT;
+  const int64_t n_up = (n_tokens + per_cta - 1) / per_cta * per_cta;  // whole LPT groups stay convergent for the shuffles
+  for (int64_t t = int64_t(blockIdx.x) * per_cta + threadIdx.x / LPT; t < n_up; t += int64_t(gridDim.x) * per_cta) {
+    const int64_t tt = t < n_tokens ? t : n_tokens - 1;
+    const uint4 rv = ldg_nc_na(reinterpret_cast<const uint4*>(residuals + tt * PD) + sub);
+    const uint4* cent = reinterpret_cast<const uint4*>(C + int64_t(__ldg(codes + tt)) * D + sub * EPL);
+    __half2 e[NH2];
+    Decoder<NBITS>::decode16(lut, rv, cent, e);
+    const __half nrm = slice_norm<NH2, LPT>(e);
+    if (sub == 0 && t < n_tokens) out[t] = nrm;
+  }
+}
+
 template <int D, int NBITS, int QP>
 int launch_k5_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
@@ -323,7 +360,7 @@ int launch_k5_t(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
   for (int i = 0; i < 16; ++i) wp.v[i] = ix->w_perm_bits[i];
   const int64_t items = int64_t(L.B) * L.R;
   const int blocks = int(items < int64_t(ix->sm_count) * 8 ? items : int64_t(ix->sm_count) * 8);
-  kern<<<blocks, K5_THREADS, smem, st>>>(ix->centroids, ix->doc_offsets, ix->doc_codes, ix->doc_residuals, wp,
+  kern<<<blocks, K5_THREADS, smem, st>>>(ix->centroids, ix->doc_offsets, ix->doc_codes, ix->doc_residuals, ix->token_norms, wp,
                                          ws.queries(), L.Q, L.B, L.R, ws.n_rerank(), ws.rerank(), ws.exact());
   FPB_LAUNCH_CHECK("k5_maxsim");
   return FPB_OK;
@@ -355,27 +392,33 @@ int launch_k5_q(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
 
 }  // namespace
 
+int launch_token_norms(const fpb_index* ix, __half* d_out, cudaStream_t st) {
+  WPerm wp;
+  for (int i = 0; i < 16; ++i) wp.v[i] = ix->w_perm_bits[i];
+  const int blocks = ix->sm_count * 8;
+#define CALL(DD, NB)                                                                                               \
+  k5_token_norms_kernel<DD, NB><<<blocks, K5_THREADS, 0, st>>>(ix->centroids, ix->doc_codes, ix->doc_residuals, wp, \
+                                                               ix->E, d_out);
+  FPB_DISPATCH_D_NBITS(ix, CALL)
+#undef CALL
+  FPB_LAUNCH_CHECK("k5_token_norms");
+  return FPB_OK;
+}
+
 int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st) {
-  // FPB_K5 = v1 | v2 | v4 | v5 pins one implementation (A/B measurements).  v1 and v2 are bit-identical;
-  // v4/v5 feed the tensor core in a different k order (fp32 accumulation order is
-  // implementation-defined in the reference too).
-  // Default (dim 128, nbits 4): Qp <= 32 -> v4 (cfg-3: v1 2.71, v2 1.67, v5 1.51, v4 1.24 ms);
-  // 32 < Qp <= 128 -> v5 (cfg-5: v2 3.27, v5 2.50 ms); everything else -> v1.
+  // dim 128, nbits 4: Qp <= 32 -> v4 (register-resident operands, mma.sync), 32 < Qp <= 128 -> v5 (tcgen05);
+  // everything else (dim 64, nbits 2, Qp = 256, documents longer than v5's pass table) -> the generic kernel here.
+  // FPB_K5=v1 pins the generic kernel (the A/B alternative).
   static const char* pin = getenv("FPB_K5");
-  const char want = pin ? pin[1] : 0;
-  const int qp = ws.L->Qp;
+  const bool generic_only = pin && pin[1] == '1';
   bool handled = false;
   int rc = FPB_OK;
-  if (want == '5' || (!want && qp > 32)) {
+  if (!generic_only && ws.L->Qp > 32) {
     rc = launch_maxsim_v5(ix, ws, st, &handled);
     if (rc != FPB_OK || handled) return rc;
   }
-  if (want == '4' || !want) {
+  if (!generic_only) {
     rc = launch_maxsim_v4(ix, ws, st, &handled);
-    if (rc != FPB_OK || handled) return rc;
-  }
-  if (want != '1') {
-    rc = launch_maxsim_v2(ix, ws, st, &handled);
     if (rc != FPB_OK || handled) return rc;
   }
 #define CALL(DD, NB) return launch_k5_q<DD, NB>(ix, ws, st);
@@ -396,7 +439,7 @@ extern "C" int fpb_reconstruct(const fpb_index* ix, const int32_t* d_doc_ids, in
   const int blocks = min(n, ix->sm_count * 8);
 #define CALL(DD, NB)                                                                                        \
   k5_reconstruct_kernel<DD, NB><<<blocks, K5_THREADS, 0, st>>>(ix->centroids, ix->doc_offsets, ix->doc_codes, \
-                                                               ix->doc_residuals, wp, d_doc_ids, n,          \
+                                                               ix->doc_residuals, ix->token_norms, wp, d_doc_ids, n,          \
                                                                d_out_offsets, static_cast<__half*>(d_out));
   FPB_DISPATCH_D_NBITS(ix, CALL)
 #undef CALL
@@ -417,7 +460,7 @@ extern "C" int fpb_token_scores(const fpb_index* ix, const void* d_queries, int 
   const int blocks = min(n, ix->sm_count * 8);
 #define CALL(DD, NB)                                                                                          \
   k5_token_scores_kernel<DD, NB><<<blocks, K5_THREADS, 0, st>>>(                                             \
-      ix->centroids, ix->doc_offsets, ix->doc_codes, ix->doc_residuals, wp, static_cast<const __half*>(d_queries), \
+      ix->centroids, ix->doc_offsets, ix->doc_codes, ix->doc_residuals, ix->token_norms, wp, static_cast<const __half*>(d_queries), \
       Q, d_query_of, d_doc_ids, n, max_len, static_cast<__half*>(d_out));
   FPB_DISPATCH_D_NBITS(ix, CALL)
 #undef CALL

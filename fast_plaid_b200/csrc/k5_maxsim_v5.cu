@@ -119,7 +119,8 @@ __device__ __forceinline__ float v5_rcp_rn(float x) {
 
 __global__ void __launch_bounds__(V5_THREADS, 1)
 k5_maxsim_v5_kernel(const __half* __restrict__ C, const int64_t* __restrict__ doc_offsets,
-                    const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals, WPerm wp,
+                    const int32_t* __restrict__ codes, const uint8_t* __restrict__ residuals,
+                    const __half* __restrict__ norms, WPerm wp,
                     const __half* __restrict__ Qpad, int Q, int Qp, int B, int R, int docs_per_chunk,
                     const int32_t* __restrict__ n_rerank, const int32_t* __restrict__ rerank,
                     float* __restrict__ exact, int* __restrict__ counter) {
@@ -255,9 +256,11 @@ k5_maxsim_v5_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
       int g = warp;
       Raw5 raw;
       int code_nxt = 0;
+      __half nrm = __float2half(1.0f);  // the token's fp16 norm from the per-token table (derived at index load)
       if (g < n_pass) {
         const int64_t row = row_of(g);
         v5_load_raw(raw, residuals, C, row, __ldg(codes + row), j);
+        nrm = __ldg(norms + row);
         if (g + V5_NDEC < n_pass) code_nxt = __ldg(codes + row_of(g + V5_NDEC));
       }
       for (int T = 0; T < n_tiles; ++T, g += V5_NDEC) {
@@ -279,18 +282,14 @@ k5_maxsim_v5_kernel(const __half* __restrict__ C, const int64_t* __restrict__ do
             }
           }
           // ---- raw is dead: fetch pass g + 20, and the code of pass g + 40 ----
+          const float nf = __half2float(nrm);
           if (g + V5_NDEC < n_pass) {
-            v5_load_raw(raw, residuals, C, row_of(g + V5_NDEC), code_nxt, j);
+            const int64_t row = row_of(g + V5_NDEC);
+            v5_load_raw(raw, residuals, C, row, code_nxt, j);
+            nrm = __ldg(norms + row);
             if (g + 2 * V5_NDEC < n_pass) code_nxt = __ldg(codes + row_of(g + 2 * V5_NDEC));
           }
-          // ---- fp32 sum of squares, norm rounded to fp16, exact division ----
-          float2 ss2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ss2 = v5_ffma2(f[i], f[i], ss2);
-          float ss = ss2.x + ss2.y;
-          ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-          ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-          const float nf = __half2float(__float2half_rn(v5_sqrt_rn(ss)));
+          // ---- norm from the per-token table, exact division ----
           const float rcp = v5_rcp_rn(nf);
           const float2 r2 = make_float2(rcp, rcp), nneg = make_float2(-nf, -nf);
 
@@ -420,7 +419,7 @@ int launch_maxsim_v5(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* h
   const int64_t total_docs = int64_t(L.B) * L.R;
   const int64_t passes_per_doc = (ix->max_doc_len + 7) / 8;
   if (passes_per_doc < 1 || passes_per_doc > V5_MAX_PASS) {
-    *handled = false;  // a single document does not fit the pass table: v4/v2 take it
+    *handled = false;  // a single document does not fit the pass table: the generic kernel takes it
     return FPB_OK;
   }
   int docs_per_chunk = V5_MAX_DOCS;
@@ -429,7 +428,8 @@ int launch_maxsim_v5(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* h
   const int chunks = L.B * ((L.R + docs_per_chunk - 1) / docs_per_chunk);
   const int blocks = chunks < ix->sm_count ? chunks : ix->sm_count;
   k5_maxsim_v5_kernel<<<blocks, V5_THREADS, V5Smem::bytes, st>>>(
-      ix->centroids, ix->doc_offsets, ix->doc_codes, ix->doc_residuals, wp, ws.queries(), L.Q, L.Qp, L.B, L.R,
+      ix->centroids, ix->doc_offsets, ix->doc_codes, ix->doc_residuals, ix->token_norms, wp, ws.queries(), L.Q, L.Qp,
+      L.B, L.R,
       docs_per_chunk, ws.n_rerank(), ws.rerank(), ws.exact(), counter);
   FPB_LAUNCH_CHECK("k5_maxsim_v5");
   return FPB_OK;

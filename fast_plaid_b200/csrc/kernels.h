@@ -48,7 +48,7 @@ int launch_compact(const uint32_t* bitmap, const uint32_t* mask, int words, int3
 int launch_approx(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st); // K3 (flags: FPB_FLAG_APPROX_*)
 int launch_select(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K3b
 int launch_maxsim(const fpb_index* ix, const Ws& ws, cudaStream_t st);            // K5 (dispatch)
-int launch_maxsim_v2(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v2 (128/4)
+int launch_token_norms(const fpb_index* ix, __half* d_out, cudaStream_t st);      // per-token fp16 norms (index load)
 int launch_maxsim_v4(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v4 (register operands)
 int launch_maxsim_v5(const fpb_index* ix, const Ws& ws, cudaStream_t st, bool* handled);  // K5 v5 (tcgen05, 20 decode warps)
 int launch_rank(const fpb_index* ix, const Ws& ws, int top_k, int64_t* d_out_ids, float* d_out_scores,

@@ -159,7 +159,7 @@ def load_library() -> ctypes.CDLL:
         lib.fpb_abi_version.restype = i32
         lib.fpb_index_create.restype = i32
         lib.fpb_index_create.argtypes = [
-            ctypes.POINTER(vp), i32, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64,
+            ctypes.POINTER(vp), i32, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, i64,
         ]
         lib.fpb_index_destroy.restype = None
         lib.fpb_index_destroy.argtypes = [vp]
@@ -529,12 +529,14 @@ class DeviceIndex:
                 self.ivf_offsets = None
                 self.ivf_pids = None
                 n_ivf = 0
+            # derived at load: the fp16 norm of every decompressed token (2 B/token), filled by fpb_index_create
+            self.token_norms = torch.empty(max(self.num_tokens, 1), dtype=torch.float16, device=dev)
             handle = ctypes.c_void_p()
             _check(
                 self._lib.fpb_index_create(
                     ctypes.byref(handle), dev.index, self.nbits, self.dim, self.num_centroids,
                     _ptr(self.centroids), _ptr(self.bucket_weights), self.num_documents,
-                    _ptr(self.doc_offsets), _ptr(self.doc_codes), _ptr(self.doc_residuals),
+                    _ptr(self.doc_offsets), _ptr(self.doc_codes), _ptr(self.doc_residuals), _ptr(self.token_norms),
                     _ptr(self.ivf_offsets), _ptr(self.ivf_pids), n_ivf, self.max_doc_len, self.doc_id_base,
                 )
             )

@@ -54,6 +54,9 @@ int fpb_abi_version(void);
  *   d_doc_offsets     i64 [n_docs + 1], exclusive cumsum of doclens (tensor.rs:221-224)
  *   d_doc_codes       i32 [n_tokens]   (narrowed from the on-disk int64 by the loader)
  *   d_doc_residuals   u8  [n_tokens, dim*nbits/8]
+ *   d_token_norms     f16 [n_tokens]  OUTPUT, caller-owned like the other arrays: filled here with the fp16 norm of
+ *                     every decompressed token (the `norm(...)` of decompress_residuals, search.rs:86-93), which the
+ *                     MaxSim / reconstruct kernels then read instead of recomputing it per (query, document) pair
  *   d_ivf_offsets     i64 [n_centroids + 1]  or NULL for a compress_only index
  *   d_ivf_pids        i32 [n_ivf]            (LOCAL doc ids, ascending within a list)
  *   doc_id_base       global id of local doc 0 (document sharding; 0 on one GPU)
@@ -64,7 +67,7 @@ int fpb_abi_version(void);
 int fpb_index_create(fpb_index** out, int device, int nbits, int dim, int64_t n_centroids,
                      const void* d_centroids, const void* d_bucket_weights, int64_t n_docs,
                      const int64_t* d_doc_offsets, const int32_t* d_doc_codes,
-                     const uint8_t* d_doc_residuals, const int64_t* d_ivf_offsets,
+                     const uint8_t* d_doc_residuals, void* d_token_norms, const int64_t* d_ivf_offsets,
                      const int32_t* d_ivf_pids, int64_t n_ivf, int64_t max_doc_len,
                      int64_t doc_id_base);
 void fpb_index_destroy(fpb_index* index);

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(engine.EXPORTED_SYMBOLS) == declared, "engine.EXPORTED_SYMBOLS is out of sync with the header"
-    assert lib.fpb_abi_version() == 5
+    assert lib.fpb_abi_version() == 6
 
 
 def test_struct_layouts_match_the_header():
@@ -42,10 +42,10 @@ def test_errors_are_reported_not_thrown():
     lib = engine.load_library()
     handle = ctypes.c_void_p()
     # unsupported nbits is rejected before any CUDA call, with a message
-    rc = lib.fpb_index_create(ctypes.byref(handle), 0, 3, 128, 16, None, None, 0, None, None, None, None, None, 0, 0, 0)
+    rc = lib.fpb_index_create(ctypes.byref(handle), 0, 3, 128, 16, None, None, 0, None, None, None, None, None, None, 0, 0, 0)
     assert rc == engine.FPB_ERR_UNSUPPORTED
     assert b"nbits" in lib.fpb_last_error()
-    rc = lib.fpb_index_create(ctypes.byref(handle), 0, 4, 100, 16, None, None, 0, None, None, None, None, None, 0, 0, 0)
+    rc = lib.fpb_index_create(ctypes.byref(handle), 0, 4, 100, 16, None, None, 0, None, None, None, None, None, None, 0, 0, 0)
     assert rc == engine.FPB_ERR_UNSUPPORTED and b"dim" in lib.fpb_last_error()
     rc = lib.fpb_workspace_layout(None, 1, 1, None, None)
     assert rc == engine.FPB_ERR_INVALID

@@ -285,7 +285,10 @@ def test_token_score_matrices_match_the_oracle(name, cuda_device):
         n = ref.shape[1]
         got = mats[k, :n, :].transpose(0, 1)
         dlt = fp16_ulp_diff(got, ref)
-        assert int(dlt.max()) <= 1, f"pair {k}: token scores differ by {int(dlt.max())} fp16 ulps"
+        # one fp16 ulp, or -- for dot products that cancel to almost zero, where an ulp is 6e-8 -- the absolute
+        # noise of summing 128 fp32 products in a different order (<= 128 * 2^-24 * sum|terms| ~ 1e-5)
+        off = (dlt > 1) & ((got.float() - ref.float()).abs() > 1e-5)
+        assert not bool(off.any()), f"pair {k}: token scores differ by {int(dlt.max())} fp16 ulps"
         bad += int((dlt > 0).sum())
         tot += dlt.numel()
         assert float(mats[k, n:, :].abs().max() if mats.shape[1] > n else 0.0) == 0.0  # rows past the document stay zero
