@@ -244,7 +244,7 @@ def traffic_for(config: str, world: int):
 
 # ----------------------------------------------------------------------------------------
 def run_b200(args) -> dict:
-    from fast_plaid_b200.engine import FPB_FLAG_APPROX_DIRECT, DeviceIndex, IndexTensors, _check
+    from fast_plaid_b200.engine import FPB_FLAG_APPROX_DIRECT, DeviceIndex, IndexTensors, ShardComm, _check, shard_grid
     from fast_plaid_b200.search.fast_plaid import FastPlaid
 
     rank, world, local = dist_setup()
@@ -256,7 +256,12 @@ def run_b200(args) -> dict:
     torch.cuda.set_device(local)
     cfg = CONFIGS[args.config]
     n_docs = cfg["n_docs"]
-    lo, hi = (n_docs * rank) // world, (n_docs * (rank + 1)) // world
+    # the grid of the sharded search: query groups x document shards (csrc/comm.cu).  Default: half the ranks'
+    # worth of query groups from 4 GPUs up (K1 and the probe then run on B / groups queries per GPU), plain document
+    # sharding below.
+    n_groups = args.query_groups or (world // 2 if world >= 4 else 1)
+    group, doc_shard, n_shards = shard_grid(rank, world, n_groups)
+    lo, hi = (n_docs * doc_shard) // n_shards, (n_docs * (doc_shard + 1)) // n_shards
     synth = load_synthetic_module()
     t0 = time.time()
     arrays, base = synth.synthetic_arrays(n_docs, cfg["doc_len"], DIM, NBITS, device, SEED_INDEX, doc_range=(lo, hi),
@@ -345,11 +350,29 @@ def run_b200(args) -> dict:
             dist.barrier()
         torch.cuda.synchronize()
 
+    comm = ShardComm.from_process_group(device) if world > 1 else None
+
+    if world > 1:
+        # N > 1: the timed step is the product path -- ONE C-ABI call per batch, both ncclAllGather issued inside on
+        # the search stream (fpb_search_batch_sharded).  The per-stage table comes from a separate staged pass.
+        stage_names = ["whole_call"]
+
+        def one_step(qb: torch.Tensor, events: list | None) -> None:  # noqa: F811
+            if events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                events.append(e0)
+            didx.search_sharded(comm, n_groups, qb, params)
+            if events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                events.append(e1)
+
     for w in range(args.warmup):
         one_step(q_dev16[w % N_QUERY_BATCHES], None)
     barrier()
 
-    didx.views(buf, lay)["stats"].zero_()  # counters of the approximate stage: timed steps only
+    (didx.views(*didx.workspace(-(-B // n_groups), Q, params)) if world > 1 else didx.views(buf, lay))["stats"].zero_()  # approximate-stage counters: timed steps only
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -368,6 +391,8 @@ def run_b200(args) -> dict:
         for i in range(len(stage_names)):
             stage_ms[i] += ev[i].elapsed_time(ev[i + 1])
     stage_ms = [x / args.steps for x in stage_ms]
+    if world > 1:  # the sharded call lays the workspace out for this rank's slice of the batch
+        buf, lay = didx.workspace(-(-B // n_groups), Q, params)
     views = didx.views(buf, lay)
     ms_bytes = maxsim_algorithmic_bytes(didx, views, lay)
     ap_hbm, ap_tokens = approx_algorithmic_bytes(didx, views, lay)
@@ -376,7 +401,8 @@ def run_b200(args) -> dict:
     n_refine_mean = float(views["n_refine"].float().mean()) if args.approx != "direct" else None
 
     # ---- e2e: FastPlaid.search(fp32 host queries) -> Python lists, copies inside the timed region ----
-    fp = FastPlaid.from_device_index(didx, shard=(rank, world) if world > 1 else None)
+    fp = FastPlaid.from_device_index(didx, shard=(rank, world) if world > 1 else None, query_groups=n_groups)
+    fp._comm = comm  # one communicator for the device-timed and the end-to-end legs
     n_full = N_FULL
 
     def e2e_call(qb_host: torch.Tensor):
@@ -402,6 +428,31 @@ def run_b200(args) -> dict:
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
 
     peak, peak_src = measured_peak_hbm()
+    if world > 1:
+        # stage breakdown of the sharded step: the local stages of this rank's slice, timed once more stage by stage
+        # (no collectives in it); the exchange cost is whole_call minus their sum
+        whole = stage_ms[0]
+        nb = max(0, min(-(-B // n_groups), B - group * -(-B // n_groups)))
+        stage_names = ["centroid_scores", "probe", "candidates", "approx", "select", "maxsim"]
+        stage_ms = [0.0] * len(stage_names)
+        if nb > 0:
+            qs = q_dev16[0][group * -(-B // n_groups): group * -(-B // n_groups) + nb].contiguous()
+            fns = [didx.stage_fn(nm, qs, params) for nm in stage_names]
+            for _ in range(3):
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)]
+                evs[0].record()
+                for i, f in enumerate(fns):
+                    f()
+                    evs[i + 1].record()
+                torch.cuda.synchronize()
+                stage_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(fns))]
+            buf, lay = didx.workspace(nb, Q, params)
+            views = didx.views(buf, lay)
+            ms_bytes = maxsim_algorithmic_bytes(didx, views, lay)
+        stage_names.append("exchange_and_merge")
+        stage_ms.append(max(0.0, whole - sum(stage_ms)))
+        stage_names.append("whole_call")
+        stage_ms.append(whole)
     i_ms = stage_names.index("maxsim")
     i_ap = stage_names.index("approx")
     ms_time = stage_ms[i_ms] / 1000.0
@@ -428,7 +479,9 @@ def run_b200(args) -> dict:
         "config": {
             "workload": f"{args.config}: {cfg['desc']}",
             "n_ivf_probe": N_IVF_PROBE, "n_full_scores": N_FULL, "reranked_per_query": lay.R,
-            "parallelism": f"document shards x{world}" + (" + 2 NCCL all-gathers (approx keys, then records of the globally surviving docs)" if world > 1 else ""),
+            "parallelism": (f"{n_groups} query groups x {n_shards} document shards, both ncclAllGather (approximate-score "
+                            "keys, then records of the globally surviving documents) issued below the C ABI"
+                            if world > 1 else "one GPU"),
             "l2": "inputs larger than L2: 20 GB index, 1.07 GB score table per batch; "
                   f"{N_QUERY_BATCHES} distinct query batches rotate across steps",
             "candidates_per_query_mean": n_cand_mean,
@@ -496,7 +549,7 @@ def count_launches(world: int, approx: str) -> int:
     hibits, prefix, bound, refine list, prefix, exact; direct: prefix, exact), select, k5, rank; sharded adds the
     key emit, the threshold, the record emit and the merge instead of the rank."""
     k3 = 2 if approx == "direct" else 7
-    return 5 + k3 + 1 + 1 + (1 if world == 1 else 4)
+    return 5 + k3 + 1 + 1 + (1 if world == 1 else 3 + max(1, world // 2))
 
 
 # ----------------------------------------------------------------------------------------
@@ -845,6 +898,8 @@ def main() -> None:
     ap.add_argument("--parity-queries", type=int, default=PARITY_QUERIES,
                     help="queries cross-checked against the oracle (rank 0, any number of GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (CPU baseline and parity sample)")
+    ap.add_argument("--query-groups", type=int, default=0,
+                    help="sharded runs: query groups of the rank grid (0 = world/2 from 4 GPUs up, else 1)")
     ap.add_argument("--approx", choices=["two-pass", "direct"], default="two-pass",
                     help="approximate stage: exact two-pass pruning (default) or the one-pass A/B alternative")
     args = ap.parse_args()

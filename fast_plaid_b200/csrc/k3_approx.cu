@@ -23,6 +23,7 @@
 //   A candidate left with an upper bound has approx <= ub < T <= the scores of >= n_full_scores/4 others:
 //   it cannot enter the pruned list whatever the tie rule, and K3b (which only orders by value) never
 //   selects it.  The pruned list and everything after it are bit-identical to scoring every candidate.
+#include <math.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -281,15 +282,22 @@ k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64
 constexpr int K3_TAU_DOCS = 64;
 constexpr int K3_TAU_THREADS = 512;
 
+// The level-1 histogram costs one shared-memory atomic per sampled value; almost all of them fall far below the
+// answer.  The smallest of the column's tile maxima (K1 writes one per 128 centroids) sits near the 94th percentile
+// of the column, well below any useful tau, so values under it are not counted; if that ever leaves fewer than the
+// wanted rank (tau would be below the floor), the level is redone without a floor.
 template <int LPR>
 __global__ void __launch_bounds__(K3_TAU_THREADS)
 k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
               const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
-              const int32_t* __restrict__ n_cand, float lambda, __half* __restrict__ tau) {
+              const int32_t* __restrict__ n_cand, const __half* __restrict__ tmax, int n_tiles, float lambda,
+              __half* __restrict__ tau) {
   constexpr int QP = LPR * 8, TPI = 32 / LPR;
   constexpr int SUBS = LPR < 4 ? LPR : 4;  // lane subs (8 columns each) handled per round
   __shared__ int hist[32][256];
   __shared__ int s_bin[32], s_rem[32];
+  __shared__ uint32_t s_floor[32];
+  __shared__ int s_redo;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane % LPR, grp = lane / LPR;
   uint16_t* out = reinterpret_cast<uint16_t*>(tau) + int64_t(b) * QP;
@@ -302,9 +310,26 @@ k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __r
   for (int g0 = 0; g0 < LPR; g0 += SUBS) {
     const bool mine = sub >= g0 && sub < g0 + SUBS;
     const int qrow = (sub - g0) * 8;  // first of this lane's 8 histogram rows
+    // floor of the round's columns: the smallest tile maximum (one warp per column)
+    for (int col = warp; col < SUBS * 8; col += K3_TAU_THREADS / 32) {
+      const int q = g0 * 8 + col;
+      uint32_t mn = 0xffffu;
+      if (q < Q) {
+        const uint16_t* tm = reinterpret_cast<const uint16_t*>(tmax) + (int64_t(b) * QP + q) * n_tiles;
+        for (int i = lane; i < n_tiles; i += 32) mn = min(mn, f16_key(tm[i]));
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+      if (lane == 0) s_floor[col] = mn;
+    }
+    if (tid == 0) s_redo = 0;
+    __syncthreads();
     for (int level = 0; level < 2; ++level) {
       for (int i = tid; i < 32 * 256; i += K3_TAU_THREADS) (&hist[0][0])[i] = 0;
       __syncthreads();
+      uint32_t fl[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fl[e] = (mine && !s_redo) ? s_floor[qrow + e] : 0u;
       for (int j = warp; j < ns; j += K3_TAU_THREADS / 32) {
         const int d = cb[int64_t(j) * n / ns];
         const int64_t o0 = doc_offsets[d];
@@ -322,7 +347,7 @@ k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __r
               for (int e = 0; e < 8; ++e) {
                 const uint32_t key = f16_key(uint16_t(w[e >> 1] >> ((e & 1) * 16)));
                 if (level == 0) {
-                  atomicAdd(&hist[qrow + e][key >> 8], 1);
+                  if (key >= fl[e]) atomicAdd(&hist[qrow + e][key >> 8], 1);
                 } else if (int(key >> 8) == s_bin[qrow + e]) {
                   atomicAdd(&hist[qrow + e][key & 255u], 1);
                 }
@@ -342,6 +367,10 @@ k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __r
         if (level == 0) {
           s_bin[tid] = bin;
           s_rem[tid] = need - cum;
+          // fewer counted values than the wanted rank although a floor was applied: count everything once more
+          if (bin == 0 && cum + hist[tid][0] < need && !s_redo && tid < SUBS * 8 && g0 * 8 + tid < Q &&
+              s_floor[tid] != 0u)
+            atomicExch(&s_redo, 2);
         } else {
           const int q = g0 * 8 + tid;
           if (q < QP) {
@@ -355,6 +384,12 @@ k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __r
         }
       }
       __syncthreads();
+      if (level == 0 && s_redo == 2) {  // CTA-uniform: the floor hid too much, redo level 0 without it
+        __syncthreads();
+        if (tid == 0) s_redo = 1;
+        __syncthreads();
+        level = -1;
+      }
     }
   }
 }
@@ -1080,15 +1115,17 @@ int launch_k3_exact(const fpb_index* ix, const Ws& ws, const int32_t* list, cons
   return FPB_OK;
 }
 
-// LAMBDA of k3_tau_kernel: the expected number of tokens per candidate and column at or above tau.  FPB_K3_LAMBDA
-// overrides it (tuning only: every value gives the same results).
-float k3_tau_lambda() {
-  static const float v = [] {
+// LAMBDA of k3_tau_kernel: the expected number of tokens per candidate and column at or above tau.  A document is
+// resolved when all of its Q columns are, so the useful level grows with log Q: LAMBDA = ln(Q) - 1.45 (2.0 at
+// Q = 32, 2.7 at Q = 64; measured optimum on cfg-3, within 10 % of it on cfg-5).  FPB_K3_LAMBDA overrides it
+// (tuning only: every value gives the same results).
+float k3_tau_lambda(int Q) {
+  static const float pinned = [] {
     const char* e = getenv("FPB_K3_LAMBDA");
-    const float x = e ? float(atof(e)) : 1.6f;
-    return x < 0.01f ? 0.01f : (x > 64.f ? 64.f : x);
+    return e ? float(atof(e)) : 0.f;
   }();
-  return v;
+  const float x = pinned > 0.f ? pinned : logf(float(Q < 2 ? 2 : Q)) - 1.45f;
+  return x < 0.5f ? 0.5f : (x > 64.f ? 64.f : x);
 }
 
 template <int LPR>
@@ -1101,7 +1138,8 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
     return launch_k3_exact<LPR>(ix, ws, nullptr, nullptr, ws.work(), st);
   }
   k3_tau_kernel<LPR><<<L.B, K3_TAU_THREADS, 0, st>>>(ws.S(), ix->K, L.Q, ix->doc_offsets, ix->doc_codes, ws.cand(),
-                                                     L.cand_cap, ws.n_cand(), k3_tau_lambda(), ws.tau());
+                                                     L.cand_cap, ws.n_cand(), ws.tmax(), L.n_tiles, k3_tau_lambda(L.Q),
+                                                     ws.tau());
   FPB_LAUNCH_CHECK("k3_tau");
   {
     dim3 grid(unsigned((ix->K + 255) / 256), unsigned(L.B));

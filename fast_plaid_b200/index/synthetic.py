@@ -147,10 +147,20 @@ class SyntheticDocuments:
     the builder size things without touching the data."""
 
     def __init__(self, n_docs: int, doc_len: int, dim: int = 128, seed: int = 7, device: str = "cuda:0",
-                 block: int = 2048, ragged: bool = False) -> None:
+                 block: int = 2048, ragged: bool = False, clusters: int = 0, spread: float = 0.03) -> None:
+        """`clusters` > 0 draws every token around one of that many random unit directions (+ `spread` * randn per
+        dimension, renormalised) -- embeddings of a real encoder are clustered, which is what k-means centroids and
+        the IVF probe rely on; 0 gives unstructured unit vectors."""
         self.n_docs, self.doc_len, self.dim, self.seed = int(n_docs), int(doc_len), int(dim), int(seed)
         self.device = torch.device(device)
         self.block = int(block)
+        self.spread = float(spread)
+        self.centers = None
+        if clusters > 0:
+            gc = torch.Generator(device=self.device)
+            gc.manual_seed(seed * 7 + 3)
+            self.centers = torch.nn.functional.normalize(
+                torch.randn(int(clusters), dim, generator=gc, device=self.device), dim=-1)
         if ragged:
             g = torch.Generator().manual_seed(seed + 1)
             self.doc_lengths = torch.randint(max(1, doc_len // 4), doc_len + 1, (n_docs,), generator=g)
@@ -167,6 +177,9 @@ class SyntheticDocuments:
         g = torch.Generator(device=self.device)
         g.manual_seed(self.seed * 1_000_003 + bi)
         x = torch.randn(self.block, self.doc_len, self.dim, generator=g, device=self.device)
+        if self.centers is not None:
+            which = torch.randint(0, self.centers.shape[0], (self.block, self.doc_len), generator=g, device=self.device)
+            x = self.centers[which] + self.spread * x
         x = torch.nn.functional.normalize(x, dim=-1).half()
         self._cache = (bi, x)
         return x

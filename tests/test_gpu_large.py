@@ -134,7 +134,7 @@ def test_cfg2_built_by_create_searches_like_the_oracle(tmp_path, cuda_device):
     from fast_plaid_b200.index.synthetic import SyntheticDocuments
 
     n_docs, doc_len, B, Q, top_k = 100_000, 300, 64, 32, 100
-    docs = SyntheticDocuments(n_docs, doc_len, device=cuda_device, seed=11)
+    docs = SyntheticDocuments(n_docs, doc_len, device=cuda_device, seed=11, clusters=8192)
     path = str(tmp_path / "cfg2")
     fp = search.FastPlaid(path, device=cuda_device)
     t0 = time.time()
@@ -147,7 +147,7 @@ def test_cfg2_built_by_create_searches_like_the_oracle(tmp_path, cuda_device):
     g = torch.Generator().manual_seed(5)
     src = torch.randint(0, n_docs, (B,), generator=g).tolist()
     queries = torch.stack([torch.nn.functional.normalize(
-        docs[d].float().cpu()[torch.randint(0, doc_len, (Q,), generator=g)] + 0.2 * torch.randn(Q, 128, generator=g), dim=-1)
+        docs[d].float().cpu()[torch.randint(0, doc_len, (Q,), generator=g)] + 0.05 * torch.randn(Q, 128, generator=g), dim=-1)
         for d in sorted(src)])
     t0 = time.time()
     res = fp.search(queries, top_k=top_k)
