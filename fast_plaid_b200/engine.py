@@ -550,6 +550,10 @@ class DeviceIndex:
         # that want concurrent searches on one GPU give each thread its own workspace through the C ABI.)
         self._search_lock = threading.RLock()
         self._last_stream: torch.cuda.Stream | None = None
+        # approximate-stage mode of the host-buffer path (results are identical in both; see _adapt_approx_mode)
+        self._approx_direct = False
+        self._approx_calls = 0
+        self._approx_hold = 0
 
     @contextlib.contextmanager
     def _exclusive(self):
@@ -758,8 +762,9 @@ class DeviceIndex:
             k = params.top_k
             return (torch.empty((0, k), dtype=torch.int64), torch.empty((0, k), dtype=torch.float32),
                     torch.empty((0,), dtype=torch.int32))
-        step = self.max_queries_per_call(Q, params)
         with self._exclusive(), torch.cuda.device(self.device):
+            params = self._approx_flags(params)
+            step = self.max_queries_per_call(Q, params)
             io = self._host_io(B, Q, params.top_k)
             self._cast_into_pinned(queries_host, io["h_q"])
             queries_host = io["h_q"]
@@ -775,6 +780,7 @@ class DeviceIndex:
                         io["h_counts"][s:e].data_ptr(), self._stream(),
                     )
                 )
+            self._adapt_approx_mode(buf, lay)
             # the pinned result buffers are reused by the next call of this shape: hand out copies (77 KB at
             # 64 x 100) while this call still owns them
             return io["h_ids"].clone(), io["h_scores"].clone(), io["h_counts"].clone()
@@ -794,6 +800,38 @@ class DeviceIndex:
                 )
             )
         return rec
+
+    # -- approximate-stage mode --------------------------------------------------------------
+    # The two-pass approximate stage (bound pass + exact pass, csrc/k3_approx.cu) wins when most candidates can be
+    # discarded by their upper bound (uniform codes: < 1 % re-scored) and loses its fixed costs when the candidates
+    # of a query all score alike (strongly clustered corpora: the exact pass then re-scores most of them).  Both
+    # modes give bit-identical results, so the host-buffer path simply looks, every APPROX_PROBE_EVERY calls, at the
+    # fraction the exact pass re-scored and holds the one-pass mode for a while when it is high.
+    APPROX_PROBE_EVERY = 8
+    APPROX_DIRECT_ABOVE = 0.30
+    APPROX_HOLD_CALLS = 64
+
+    def _approx_flags(self, params: FpbParams) -> FpbParams:
+        if self._approx_direct and not (params.flags & (FPB_FLAG_APPROX_EXACT_ALL | FPB_FLAG_APPROX_DIRECT)):
+            return self.with_flags(params, FPB_FLAG_APPROX_DIRECT)
+        return params
+
+    def _adapt_approx_mode(self, buf: torch.Tensor, lay: FpbLayout) -> None:
+        """Called after a synchronised host-buffer search (the workspace still holds its counters)."""
+        if self._approx_direct:
+            self._approx_hold -= 1
+            if self._approx_hold <= 0:
+                self._approx_direct = False  # probe the two-pass mode again
+            return
+        self._approx_calls += 1
+        if self._approx_calls % self.APPROX_PROBE_EVERY or lay.flags & FPB_FLAG_APPROX_DIRECT:
+            return
+        v = self.views(buf, lay)
+        both = torch.stack([v["n_refine"].sum(), v["n_cand"].sum()]).cpu()
+        n_ref, n_cand = int(both[0]), int(both[1])
+        if n_cand > 0 and n_ref / n_cand > self.APPROX_DIRECT_ABOVE:
+            self._approx_direct = True
+            self._approx_hold = self.APPROX_HOLD_CALLS
 
     # the whole sharded search in one C-ABI call (both NCCL all-gathers issued inside, csrc/comm.cu)
     def _sharded_io(self, comm: ShardComm, n_query_groups: int, B: int, Q: int, params: FpbParams):

@@ -192,6 +192,28 @@ def test_one_rank_communicator_runs_the_sharded_c_path(cuda_device):
     fp.close()
 
 
+def test_adaptive_approx_mode_switches_without_changing_results(cuda_device):
+    """The host path re-examines, every few calls, how much the exact pass of the two-pass approximate stage had to
+    re-score and holds the one-pass mode when that is high; both modes must return the same bytes."""
+    from fast_plaid_b200.engine import DeviceIndex
+
+    docs = make_docs(800, 10, 60, seed=51)
+    oidx, _ = build_oracle_index(docs)
+    didx = DeviceIndex(to_index_tensors(oidx), cuda_device)
+    queries = make_queries(6, 32, seed=52, docs=docs)
+    params = DeviceIndex.make_params(10, 256, 8)
+    base = didx.search_host(queries, params)
+    didx.APPROX_PROBE_EVERY, didx.APPROX_DIRECT_ABOVE, didx.APPROX_HOLD_CALLS = 1, -1.0, 3  # force the switch
+    assert not didx._approx_direct
+    r1 = didx.search_host(queries, params)  # two-pass call that trips the switch
+    assert didx._approx_direct
+    for _ in range(3):  # held one-pass calls
+        r = didx.search_host(queries, params)
+        assert all(torch.equal(x, y) for x, y in zip(r, base))
+    assert not didx._approx_direct  # probing the two-pass mode again
+    assert all(torch.equal(x, y) for x, y in zip(r1, base))
+
+
 def test_sharded_subset_search_equals_the_unsharded_subset_search(cuda_device):
     """subset= with documents sharded: the centroid bitmaps of the shards are OR-ed (the all-gather is
     emulated by stacking, all shards live on one device) and the result must equal the single-index
