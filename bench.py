@@ -740,11 +740,15 @@ def parity_sample(po, oidx, queries_host, params, gpu, world: int) -> dict:
             ka = torch.where(a < 0, -(a & 0x7FFF), a)
             kr = torch.where(r < 0, -(r & 0x7FFF), r)
             dlt = (ka - kr).abs()
-            s_ulp_max = max(s_ulp_max, int(dlt.max()))
+            # near zero an fp16 ulp shrinks to 6e-8 while the order-of-summation noise of a 128-term fp32 dot
+            # product stays ~1e-5 absolute: entries that differ by more than one ulp must be inside that noise
+            far = (dlt > 1) & ((S_gpu[i].float() - pure["S"].float()).abs() > 2e-5)
+            s_ulp_max = max(s_ulp_max, int(dlt[(S_gpu[i].float().abs() > 1e-2)].max()) if bool((S_gpu[i].float().abs() > 1e-2).any()) else 0)
             s_diff_entries += int((dlt > 0).sum())
             s_entries += dlt.numel()
-            if int(dlt.max()) > 1:
-                unexplained.append(f"q{i}: S differs from the oracle by {int(dlt.max())} fp16 ulps")
+            if bool(far.any()):
+                unexplained.append(f"q{i}: S differs from the oracle by {int(dlt[far].max())} fp16 ulps / "
+                                   f"{float((S_gpu[i].float() - pure['S'].float()).abs().max()):.2e} absolute")
         # -- integer stages given S (one GPU: read from the workspace; sharded: implied by the final result)
         if "cells" in gpu:
             cg = torch.unique(gpu["cells"][i].flatten().long())
@@ -807,7 +811,7 @@ def parity_sample(po, oidx, queries_host, params, gpu, world: int) -> dict:
     return {"queries": n, "n_gpus": world,
             "identical_id_lists": identical, "identical_id_lists_given_gpu_S": identical_given_s,
             "mean_topk_overlap": overlap / max(1, n),
-            "S_max_fp16_ulp": s_ulp_max, "S_entries_differing": s_diff_entries, "S_entries": s_entries,
+            "S_max_fp16_ulp_above_1e-2": s_ulp_max, "S_entries_differing": s_diff_entries, "S_entries": s_entries,
             "max_rel_score_err_given_S": max_rel,
             "differing_docs_by_cause": classes,
             "unexplained_mismatches": len(unexplained), "unexplained": unexplained[:8],

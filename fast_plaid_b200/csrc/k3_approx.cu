@@ -337,11 +337,24 @@ k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __r
         for (int base = 0; base < len; base += 32) {
           const int t = base + lane;
           const int code = (t < len) ? __ldg(codes + o0 + t) : -1;
+          // all LPR row gathers of the window go out before the first histogram update (the kernel is a chain of
+          // dependent latencies otherwise: 0.33 ms with the loads issued one per update round)
+          constexpr int JB = LPR < 8 ? LPR : 8;  // gathers in flight per lane
+#pragma unroll 1
+          for (int j0 = 0; j0 < LPR; j0 += JB) {
+          uint4 vv[JB];
+          int cc[JB];
 #pragma unroll
-          for (int jj = 0; jj < LPR; ++jj) {
-            const int c = __shfl_sync(0xffffffffu, code, jj * TPI + grp);
+          for (int jj = 0; jj < JB; ++jj) {
+            cc[jj] = __shfl_sync(0xffffffffu, code, (j0 + jj) * TPI + grp);
+            vv[jj] = make_uint4(0u, 0u, 0u, 0u);
+            if (cc[jj] >= 0 && mine) vv[jj] = __ldg(Sb + int64_t(cc[jj]) * LPR + sub);
+          }
+#pragma unroll
+          for (int jj = 0; jj < JB; ++jj) {
+            const int c = cc[jj];
             if (c >= 0 && mine) {
-              const uint4 v = __ldg(Sb + int64_t(c) * LPR + sub);
+              const uint4 v = vv[jj];
               const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -353,6 +366,7 @@ k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __r
                 }
               }
             }
+          }
           }
         }
       }
@@ -444,8 +458,33 @@ __device__ __forceinline__ uint32_t k3_lds(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void k3_sts_if(uint32_t addr, uint32_t v, uint32_t pred) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p st.shared.u32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
+// One window's queue step in a single block so that the bit is tested ONCE: p = bit c of the bitmap word, ballot,
+// rank of this lane among the set lanes, predicated store of the code into the ring.  The ring is aligned to its
+// size, so "position modulo the ring, plus its base" is one logic op.  Returns the ballot; tail_bytes is the
+// warp-uniform fill pointer in bytes.
+__device__ __forceinline__ unsigned k3_push(uint32_t word, uint32_t code, uint32_t ring_base, uint32_t ring_mask_bytes,
+                                            uint32_t tail_bytes, uint32_t lt_mask) {
+  unsigned mask;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t, r;\n"
+      "shf.r.wrap.b32 t, %1, 0, %2;\n"   // word >> (code & 31)
+      "and.b32 t, t, 1;\n"
+      "setp.ne.u32 p, t, 0;\n"
+      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+      "and.b32 r, %0, %6;\n"
+      "popc.b32 r, r;\n"
+      "shl.b32 r, r, 2;\n"
+      "add.u32 r, r, %5;\n"
+      "and.b32 r, r, %4;\n"
+      "or.b32 r, r, %3;\n"
+      "@p st.shared.u32 [r], %2;\n"
+      "}"
+      : "=r"(mask)
+      : "r"(word), "r"(code), "r"(ring_base), "r"(ring_mask_bytes), "r"(tail_bytes), "r"(lt_mask)
+      : "memory");
+  return mask;
 }
 
 template <int LPR, int MINB, int W, int U, bool FULLQ>
@@ -468,7 +507,8 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane % LPR, grp = lane / LPR;
   const uint32_t sb_bm = smem_u32(k3_smem);
-  const uint32_t sb_wq = sb_bm + uint32_t(hb_words + 4) * 4u + uint32_t(warp) * (WQ * 4u);
+  // rings: aligned to their size (WQ * 4 bytes) so that k3_push can OR the base in
+  const uint32_t sb_wq = ((sb_bm + uint32_t(hb_words + 4) * 4u + (WQ * 4u - 1u)) & ~(WQ * 4u - 1u)) + uint32_t(warp) * (WQ * 4u);
   const int INV = hb_words * 32;  // a code whose bit lives in the spare zero word
   unsigned lt_mask;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
@@ -561,9 +601,7 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
       for (int u = 0; u < W; ++u) wbit[u] = k3_lds(sb_bm + ((uint32_t(c[u]) >> 5) << 2));
 #pragma unroll
       for (int u = 0; u < W; ++u) {
-        const uint32_t bit = __funnelshift_r(wbit[u], 0u, uint32_t(c[u])) & 1u;  // shift by c mod 32
-        const unsigned mask = __ballot_sync(0xffffffffu, bit != 0u);
-        k3_sts_if(sb_wq + (((tail + __popc(mask & lt_mask)) & (WQ - 1)) << 2), uint32_t(c[u]), bit);
+        const unsigned mask = k3_push(wbit[u], uint32_t(c[u]), sb_wq, WQ * 4u - 1u, tail << 2, lt_mask);
         tail += __popc(mask);
       }
       __syncwarp();
@@ -1166,7 +1204,7 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
       default: kern = K3_BOUND(4, 6, 4); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
     }
 #undef K3_BOUND
-    const size_t smem = size_t(L.hb_words + 4) * 4 + size_t(K3_THREADS / 32) * wq * 4;
+    const size_t smem = size_t(L.hb_words + 4) * 4 + size_t(K3_THREADS / 32 + 1) * wq * 4;  // + alignment slack of the rings
     FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)
     int per_sm = int((227 * 1024) / (smem + 1024 + 2048));

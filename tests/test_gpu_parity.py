@@ -285,9 +285,11 @@ def test_token_score_matrices_match_the_oracle(name, cuda_device):
         n = ref.shape[1]
         got = mats[k, :n, :].transpose(0, 1)
         dlt = fp16_ulp_diff(got, ref)
-        # one fp16 ulp, or -- for dot products that cancel to almost zero, where an ulp is 6e-8 -- the absolute
-        # noise of summing 128 fp32 products in a different order (<= 128 * 2^-24 * sum|terms| ~ 1e-5)
-        off = (dlt > 1) & ((got.float() - ref.float()).abs() > 1e-5)
+        # one fp16 ulp, or -- for dot products that cancel to almost zero, where an ulp is as small as 6e-8 -- an
+        # absolute 1e-4: summing 128 fp32 products in a different order moves a result by <= 128 * 2^-24 * sum|terms|
+        # ~ 1e-5, and a token whose fp16 norm lands one ulp away (its fp32 sum of squares is accumulated in a
+        # different order too) has each of its 128 normalised elements re-rounded: ~ sqrt(128) * 2^-11 * |term|
+        off = (dlt > 1) & ((got.float() - ref.float()).abs() > 1e-4)
         assert not bool(off.any()), f"pair {k}: token scores differ by {int(dlt.max())} fp16 ulps"
         bad += int((dlt > 0).sum())
         tot += dlt.numel()
