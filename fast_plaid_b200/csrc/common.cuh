@@ -38,10 +38,6 @@ struct fpb_index {
   // (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint; has_tmap = 0 if unavailable)
   alignas(64) unsigned char tmap_centroids[128];
   int has_tmap;
-  // L2 residency of the centroid table during the MaxSim kernel (cudaLaunchAttributeAccessPolicyWindow): window size
-  // and the fraction of it the persisting carve-out can hold; 0 bytes = the device offers none
-  size_t l2_window_bytes;
-  float l2_hit_ratio;
 };
 
 struct WPerm {

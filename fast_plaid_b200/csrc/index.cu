@@ -111,20 +111,6 @@ extern "C" int fpb_index_create(fpb_index** out, int device, int nbits, int dim,
     return FPB_ERR_CUDA;
   }
   ix->sm_count = prop.multiProcessorCount;
-  {  // persisting-L2 carve-out for the centroid table (67 MB at K = 262144; B200 L2: 126 MB)
-    const size_t table = size_t(n_centroids) * dim * 2;
-    size_t persist = size_t(prop.persistingL2CacheMaxSize) < table ? size_t(prop.persistingL2CacheMaxSize) : table;
-    ix->l2_window_bytes = 0;
-    ix->l2_hit_ratio = 0.f;
-    if (persist > 0 && prop.accessPolicyMaxWindowSize > 0 &&
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
-      ix->l2_window_bytes = table < size_t(prop.accessPolicyMaxWindowSize) ? table : size_t(prop.accessPolicyMaxWindowSize);
-      const float r = float(double(persist) / double(ix->l2_window_bytes));
-      ix->l2_hit_ratio = r > 1.f ? 1.f : r;
-    } else {
-      cudaGetLastError();
-    }
-  }
   uint16_t w[16];
   e = cudaMemcpy(w, d_bucket_weights, sizeof(uint16_t) * (1 << nbits), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) {

@@ -310,6 +310,7 @@ k3_tau_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __r
   for (int g0 = 0; g0 < LPR; g0 += SUBS) {
     const bool mine = sub >= g0 && sub < g0 + SUBS;
     const int qrow = (sub - g0) * 8;  // first of this lane's 8 histogram rows
+    __syncthreads();  // the previous round's last reads of s_redo / s_floor / s_bin are done
     // floor of the round's columns: the smallest tile maximum (one warp per column)
     for (int col = warp; col < SUBS * 8; col += K3_TAU_THREADS / 32) {
       const int q = g0 * 8 + col;

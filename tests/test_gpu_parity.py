@@ -279,18 +279,21 @@ def test_token_score_matrices_match_the_oracle(name, cuda_device):
     mats = didx.token_scores(q16, torch.tensor([p[0] for p in pairs], dtype=torch.int32),
                              torch.tensor([p[1] for p in pairs], dtype=torch.int32)).cpu()
     torch.cuda.synchronize()
-    bad = tot = 0
+    bad = tot = far = 0
     for k, (b, d) in enumerate(pairs):
         ref = oracle_token_matrix(oidx, queries[b], d)  # [Q, len]
         n = ref.shape[1]
         got = mats[k, :n, :].transpose(0, 1)
         dlt = fp16_ulp_diff(got, ref)
-        # one fp16 ulp, or -- for dot products that cancel to almost zero, where an ulp is as small as 6e-8 -- an
-        # absolute 1e-4: summing 128 fp32 products in a different order moves a result by <= 128 * 2^-24 * sum|terms|
-        # ~ 1e-5, and a token whose fp16 norm lands one ulp away (its fp32 sum of squares is accumulated in a
-        # different order too) has each of its 128 normalised elements re-rounded: ~ sqrt(128) * 2^-11 * |term|
-        off = (dlt > 1) & ((got.float() - ref.float()).abs() > 1e-4)
-        assert not bool(off.any()), f"pair {k}: token scores differ by {int(dlt.max())} fp16 ulps"
+        # One fp16 ulp -- except for dot products that cancel to almost zero, where an ulp shrinks to 6e-8 while the
+        # noise stays absolute: summing 128 fp32 products in a different order (~1e-5), and, for a token whose fp16
+        # norm lands one ulp away, the re-rounding of each of its 128 normalised elements (up to 128 * 2^-11 * |term|,
+        # a few 1e-4 at worst).  Such entries must stay within 1e-3 absolute and be rare; they never decide a MaxSim
+        # (the maximum over tokens is nowhere near zero).
+        off = dlt > 1
+        assert float((got.float() - ref.float()).abs()[off].max() if bool(off.any()) else 0.0) <= 1e-3, \
+            f"pair {k}: token scores differ by {int(dlt.max())} fp16 ulps"
+        far += int(off.sum())
         bad += int((dlt > 0).sum())
         tot += dlt.numel()
         assert float(mats[k, n:, :].abs().max() if mats.shape[1] > n else 0.0) == 0.0  # rows past the document stay zero
@@ -298,6 +301,7 @@ def test_token_score_matrices_match_the_oracle(name, cuda_device):
         manual = float(got.float().max(dim=1).values.sum())
         assert abs(manual - float(st["scores"][b, rank])) <= 1e-3 * max(1.0, abs(manual))
     assert bad / max(tot, 1) < 5e-3, f"{bad}/{tot} token scores differ by one ulp"
+    assert far / max(tot, 1) < 1e-4, f"{far}/{tot} token scores differ by more than one ulp"
 
 
 def test_compress_only_index_refuses_search(cuda_device):

@@ -158,3 +158,32 @@ def test_sharded_subset_search_equals_single_index(world):
         assert [d for d, _ in got] == ref_ids
         assert [s for _, s in got] == ref_sc
         assert set(ref_ids) <= set(sub.tolist())
+
+
+def test_query_group_by_document_shard_grid_covers_every_query_and_document_once():
+    """csrc/comm.cu: rank r = document shard r % n_shards of query group r / n_shards; a batch of B queries is cut
+    into n_groups contiguous slices of ceil(B / n_groups) (the last may be short or empty), the documents into
+    n_shards contiguous ranges.  Every (query, document) pair must belong to exactly one rank."""
+    from fast_plaid_b200.engine import shard_grid
+
+    for world in (1, 2, 4, 8):
+        for n_groups in [g for g in (1, 2, 4, 8) if world % g == 0]:
+            n_shards = world // n_groups
+            for B, n_docs in ((64, 1000), (5, 17), (1, 3), (16, 8)):
+                b_local = -(-B // n_groups)
+                seen = {}
+                for r in range(world):
+                    g, s, ns = shard_grid(r, world, n_groups)
+                    assert ns == n_shards and 0 <= g < n_groups and 0 <= s < n_shards
+                    q0 = g * b_local
+                    qs = range(q0, min(B, q0 + b_local))
+                    ds = range((n_docs * s) // n_shards, (n_docs * (s + 1)) // n_shards)
+                    for q in qs:
+                        for d in ds:
+                            assert (q, d) not in seen, (world, n_groups, q, d)
+                            seen[(q, d)] = r
+                assert len(seen) == B * n_docs
+    import pytest
+
+    with pytest.raises(ValueError):
+        shard_grid(0, 6, 4)
