@@ -429,28 +429,82 @@ def run_b200(args) -> dict:
 
     peak, peak_src = measured_peak_hbm()
     if world > 1:
-        # stage breakdown of the sharded step: the local stages of this rank's slice, timed once more stage by stage
-        # (no collectives in it); the exchange cost is whole_call minus their sum
+        # stage breakdown of the sharded step: the same sequence once more through the step-wise entry points, the two
+        # all-gathers issued through torch.distributed here (the timed product path issues them below the C ABI)
         whole = stage_ms[0]
-        nb = max(0, min(-(-B // n_groups), B - group * -(-B // n_groups)))
-        stage_names = ["centroid_scores", "probe", "candidates", "approx", "select", "maxsim"]
-        stage_ms = [0.0] * len(stage_names)
-        if nb > 0:
-            qs = q_dev16[0][group * -(-B // n_groups): group * -(-B // n_groups) + nb].contiguous()
-            fns = [didx.stage_fn(nm, qs, params) for nm in stage_names]
-            for _ in range(3):
-                evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)]
-                evs[0].record()
-                for i, f in enumerate(fns):
-                    f()
-                    evs[i + 1].record()
-                torch.cuda.synchronize()
-                stage_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(fns))]
+        b_local = -(-B // n_groups)
+        nb = max(0, min(b_local, B - group * b_local))
+        stage_names = ["centroid_scores", "probe", "candidates", "approx", "select", "exchange_keys", "maxsim",
+                       "exchange_records_and_merge"]
+        acc = [0.0] * len(stage_names)
+        per_rank = b_local * lay.R
+        keys_l = torch.zeros((b_local, lay.R), dtype=torch.int64, device=device)
+        keys_all = torch.zeros((world, b_local, lay.R), dtype=torch.int64, device=device)
+        rec_l = torch.full((b_local, lay.R, 16), 255, dtype=torch.uint8, device=device)
+        rec_all = torch.zeros((world, b_local, lay.R, 16), dtype=torch.uint8, device=device)
+        reps = 3
+        for rep in range(reps):
+            qs = q_dev16[rep % N_QUERY_BATCHES][group * b_local: group * b_local + nb].contiguous()
+            bufs, lays = didx.workspace(max(nb, 1), Q, params)
+            pl = ctypes.byref(params)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stage_names) + 1)]
+            h = didx._handle
+            evs[0].record()
+            if nb:
+                _check(lib.fpb_stage_centroid_scores(h, qs.data_ptr(), nb, Q, pl, bufs.data_ptr(), bufs.numel(), st))
+            evs[1].record()
+            if nb:
+                _check(lib.fpb_stage_probe(h, nb, Q, pl, bufs.data_ptr(), bufs.numel(), st))
+            evs[2].record()
+            if nb:
+                _check(lib.fpb_stage_candidates(h, nb, Q, pl, bufs.data_ptr(), bufs.numel(), st))
+            evs[3].record()
+            if nb:
+                _check(lib.fpb_stage_approx(h, nb, Q, pl, bufs.data_ptr(), bufs.numel(), st))
+            evs[4].record()
+            if nb:
+                _check(lib.fpb_stage_select(h, nb, Q, pl, bufs.data_ptr(), bufs.numel(), st))
+            evs[5].record()
+            if nb:
+                _check(lib.fpb_stage_keys(h, nb, Q, pl, bufs.data_ptr(), bufs.numel(), keys_l.data_ptr(), st))
+            dist.all_gather_into_tensor(keys_all.view(-1), keys_l.view(-1))
+            if nb:
+                # the kernel strides the gathered keys by the queries per rank (b_local); this rank's group starts at
+                # shard 0 of the group
+                grp_keys = keys_all[group * n_shards:(group + 1) * n_shards]
+                if nb == b_local:
+                    _check(lib.fpb_shard_apply_threshold(h, grp_keys.data_ptr(), n_shards, doc_shard, nb, Q, pl,
+                                                         bufs.data_ptr(), bufs.numel(), st))
+                else:  # ragged last group: repack to the stride the step-wise entry point expects
+                    gk = grp_keys[:, :nb].contiguous()
+                    _check(lib.fpb_shard_apply_threshold(h, gk.data_ptr(), n_shards, doc_shard, nb, Q, pl,
+                                                         bufs.data_ptr(), bufs.numel(), st))
+            evs[6].record()
+            if nb:
+                _check(lib.fpb_stage_maxsim(h, nb, Q, pl, bufs.data_ptr(), bufs.numel(), st))
+            evs[7].record()
+            if nb:
+                _check(lib.fpb_stage_records(h, nb, Q, pl, bufs.data_ptr(), bufs.numel(), rec_l.data_ptr(), st))
+            dist.all_gather_into_tensor(rec_all.view(-1), rec_l.view(-1))
+            for g in range(n_groups):
+                gn = max(0, min(b_local, B - g * b_local))
+                if gn == 0:
+                    continue
+                gr = rec_all[g * n_shards:(g + 1) * n_shards]
+                gr = gr if gn == b_local else gr[:, :gn].contiguous()
+                _check(lib.fpb_merge_shards(gr.data_ptr(), n_shards, gn, lay.R, k, ids[g * b_local:].data_ptr(),
+                                            scores[g * b_local:].data_ptr(), counts[g * b_local:].data_ptr(), st))
+            evs[8].record()
+            torch.cuda.synchronize()
+            if rep > 0:  # the first repetition warms the step-wise path up
+                for i in range(len(stage_names)):
+                    acc[i] += evs[i].elapsed_time(evs[i + 1])
+        stage_ms = [x / (reps - 1) for x in acc]
+        if nb:
             buf, lay = didx.workspace(nb, Q, params)
             views = didx.views(buf, lay)
             ms_bytes = maxsim_algorithmic_bytes(didx, views, lay)
-        stage_names.append("exchange_and_merge")
-        stage_ms.append(max(0.0, whole - sum(stage_ms)))
+            ap_hbm, ap_tokens = approx_algorithmic_bytes(didx, views, lay)
         stage_names.append("whole_call")
         stage_ms.append(whole)
     i_ms = stage_names.index("maxsim")

@@ -2,7 +2,7 @@
 # multi-GPU pass: NCCL tests + sharded bench lines.  usage: gpu_r2h_multi.sh <ngpus>
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_multi.py tests/test_gpu_api.py -x -q > gpurun_out/r2h_tests_n$N.log 2>&1
+timeout 1200 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2h_tests_n$N.log 2>&1
 echo "tests rc=$?" >> gpurun_out/r2h_tests_n$N.log
 tail -4 gpurun_out/r2h_tests_n$N.log
 run() { name=$1; shift; timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 "$@" > gpurun_out/r2h_bench_${name}_n$N.json 2> gpurun_out/r2h_bench_${name}_n$N.err; echo "$name rc=$?"; }
@@ -13,9 +13,8 @@ if [ "$N" = "2" ]; then
 else
   run cfg3 --no-cpu-baseline
   run cfg3_g1 --no-cpu-baseline --query-groups 1
-  run cfg3_g8 --no-cpu-baseline --query-groups $N
   run cfg4 --config cfg4 --no-cpu-baseline
-  run cfg3_par --parity-queries 16
+  run cfg3_par --parity-queries 4
 fi
 for f in gpurun_out/r2h_bench_*_n$N.json; do echo $f; python - "$f" <<'PY'
 import json,sys
