@@ -30,6 +30,7 @@
 
 namespace {
 
+constexpr int64_t K3_TWO_PASS_MIN_TOKENS = 200000000;  // B * index tokens below which one pass is used by default
 constexpr int K3_THREADS = 256;
 constexpr int K3_DOCS_PER_CHUNK = 64;    // exact pass: work-queue granule
 constexpr int K3A_DOCS_PER_CHUNK = 128;  // bound pass
@@ -280,7 +281,7 @@ k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64
 // order-preserving keys.  One CTA per query; columns are handled 32 at a time.
 // ---------------------------------------------------------------------------------------
 constexpr int K3_TAU_DOCS = 64;
-constexpr int K3_TAU_THREADS = 512;
+constexpr int K3_TAU_THREADS = 1024;
 
 // The level-1 histogram costs one shared-memory atomic per sampled value; almost all of them fall far below the
 // answer.  The smallest of the column's tile maxima (K1 writes one per 128 centroids) sits near the 94th percentile
@@ -1170,8 +1171,12 @@ float k3_tau_lambda(int Q) {
 template <int LPR>
 int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
   const fpb_layout& L = *ws.L;
-  // one-pass scoring: asked for, or the K-bit map of a query does not fit next to a second CTA's
-  if ((flags & FPB_FLAG_APPROX_DIRECT) || size_t(L.hb_words) * 4 > 96 * 1024) {
+  // one-pass scoring: asked for, or the K-bit map of a query does not fit next to a second CTA's, or (nothing asked
+  // for) the job is too small to repay the fixed cost of the two passes -- results are identical in every case
+  const bool forced = (flags & (FPB_FLAG_APPROX_TWO_PASS | FPB_FLAG_APPROX_EXACT_ALL)) != 0;
+  const bool small_job = int64_t(L.B) * ix->E < K3_TWO_PASS_MIN_TOKENS;
+  if ((flags & FPB_FLAG_APPROX_DIRECT) || size_t(L.hb_words) * 4 > 96 * 1024 || (!forced && small_job)) {
+    FPB_CUDA_CHECK(cudaMemsetAsync(ws.n_refine(), 0, size_t(L.B) * 4, st));  // nothing was re-scored
     k3_prefix_kernel<<<1, 32, 0, st>>>(ws.n_cand(), L.B, K3_DOCS_PER_CHUNK, ws.work());
     FPB_LAUNCH_CHECK("k3_prefix");
     return launch_k3_exact<LPR>(ix, ws, nullptr, nullptr, ws.work(), st);
@@ -1199,9 +1204,10 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
     const bool fullq = L.Q == L.Qp;
 #define K3_BOUND(MB, WW, UU) (fullq ? k3_bound_kernel<LPR, MB, WW, UU, true> : k3_bound_kernel<LPR, MB, WW, UU, false>)
     switch (shape) {
-      case 1: kern = K3_BOUND(5, 4, 4); minb = 5; wq = K3_WQ_FOR(4, 4 * TPI); break;
-      case 2: kern = K3_BOUND(4, 12, 4); minb = 4; wq = K3_WQ_FOR(12, 4 * TPI); break;
-      case 3: kern = K3_BOUND(4, 11, 4); minb = 4; wq = K3_WQ_FOR(11, 4 * TPI); break;
+      case 1: kern = K3_BOUND(5, 6, 4); minb = 5; wq = K3_WQ_FOR(6, 4 * TPI); break;
+      case 2: kern = K3_BOUND(5, 6, 2); minb = 5; wq = K3_WQ_FOR(6, 2 * TPI); break;
+      case 3: kern = K3_BOUND(6, 6, 2); minb = 6; wq = K3_WQ_FOR(6, 2 * TPI); break;
+      case 4: kern = K3_BOUND(4, 6, 2); minb = 4; wq = K3_WQ_FOR(6, 2 * TPI); break;
       default: kern = K3_BOUND(4, 6, 4); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
     }
 #undef K3_BOUND

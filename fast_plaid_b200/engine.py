@@ -48,6 +48,7 @@ class FpbParams(ctypes.Structure):
 FPB_FLAG_SUBSET = 1
 FPB_FLAG_APPROX_EXACT_ALL = 2  # off_approx holds the exact score of every candidate (parity tests)
 FPB_FLAG_APPROX_DIRECT = 4  # one-pass approximate scoring (A/B alternative of the two-pass default)
+FPB_FLAG_APPROX_TWO_PASS = 8  # two passes even for a job the library would score in one (small batch x index)
 
 
 class FpbLayout(ctypes.Structure):
@@ -812,7 +813,8 @@ class DeviceIndex:
     APPROX_HOLD_CALLS = 64
 
     def _approx_flags(self, params: FpbParams) -> FpbParams:
-        if self._approx_direct and not (params.flags & (FPB_FLAG_APPROX_EXACT_ALL | FPB_FLAG_APPROX_DIRECT)):
+        if self._approx_direct and not (params.flags & (FPB_FLAG_APPROX_EXACT_ALL | FPB_FLAG_APPROX_DIRECT |
+                                                        FPB_FLAG_APPROX_TWO_PASS)):
             return self.with_flags(params, FPB_FLAG_APPROX_DIRECT)
         return params
 

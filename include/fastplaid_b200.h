@@ -94,9 +94,13 @@ typedef struct fpb_params {
  * bit-identical to scoring every candidate.
  *   FPB_FLAG_APPROX_EXACT_ALL : also refine the candidates below the threshold (off_approx then holds
  *                               the exact score of EVERY candidate; parity tests)
- *   FPB_FLAG_APPROX_DIRECT    : one-pass scoring of every candidate (the A/B alternative) */
+ *   FPB_FLAG_APPROX_DIRECT    : one-pass scoring of every candidate (the A/B alternative)
+ *   FPB_FLAG_APPROX_TWO_PASS  : two passes whatever the size of the job
+ * With none of them the library picks: the two passes carry ~0.5 ms of fixed cost (threshold sample, bitmap,
+ * refine list), so a call whose batch x index is too small to repay it (B * n_tokens < 2e8) is scored in one pass. */
 #define FPB_FLAG_APPROX_EXACT_ALL 2
 #define FPB_FLAG_APPROX_DIRECT 4
+#define FPB_FLAG_APPROX_TWO_PASS 8
 
 /* Byte offsets of every intermediate inside the workspace, so the parity tests can read
  * each stage (S, probed cells, candidates, approx scores, rerank list, exact scores)

@@ -203,6 +203,8 @@ def test_adaptive_approx_mode_switches_without_changing_results(cuda_device):
     queries = make_queries(6, 32, seed=52, docs=docs)
     params = DeviceIndex.make_params(10, 256, 8)
     base = didx.search_host(queries, params)
+    # (an index this small is scored in one pass anyway; the mechanism is what is under test: the probe sees
+    # n_refine / n_cand = 0 > -1 and holds the explicit one-pass flag)
     didx.APPROX_PROBE_EVERY, didx.APPROX_DIRECT_ABOVE, didx.APPROX_HOLD_CALLS = 1, -1.0, 3  # force the switch
     assert not didx._approx_direct
     r1 = didx.search_host(queries, params)  # two-pass call that trips the switch

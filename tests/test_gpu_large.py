@@ -68,10 +68,10 @@ def test_sample_against_oracle(big, cuda_device):
     oidx = po.OracleIndex(nbits=4, centroids=didx.centroids.cpu(), bucket_weights=didx.bucket_weights.cpu(),
                           ivf=didx.ivf_pids.cpu().long(), ivf_lengths=ivf_len, doc_codes=didx.doc_codes.cpu().long(),
                           doc_residuals=didx.doc_residuals.cpu(), doc_lengths=lens)
-    from fast_plaid_b200.engine import FPB_FLAG_APPROX_EXACT_ALL, DeviceIndex
+    from fast_plaid_b200.engine import FPB_FLAG_APPROX_EXACT_ALL, FPB_FLAG_APPROX_TWO_PASS, DeviceIndex
 
-    # default two-pass approximate stage first (views of the shared workspace: copy what is compared)
-    dflt = didx.run_stages(queries[:3].half().to(cuda_device), params)
+    # pruned two-pass approximate stage first (views of the shared workspace: copy what is compared)
+    dflt = didx.run_stages(queries[:3].half().to(cuda_device), DeviceIndex.with_flags(params, FPB_FLAG_APPROX_TWO_PASS))
     torch.cuda.synchronize()
     d_rerank, d_ids, d_scores = dflt["rerank"].clone(), dflt["ids"].clone(), dflt["scores"].clone()
     d_ub, d_nref = dflt["approx"].clone(), dflt["n_refine"].clone()
