@@ -135,3 +135,34 @@ def test_nccl_sharded_search_equals_unsharded(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res == 1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_replicated_devices_in_one_process_equal_a_single_device(tmp_path):
+    """The reference's own multi-GPU mode (fast_plaid.py:893-928): one process, the index replicated on every device
+    of the list, the query list split across one thread per device.  Every kernel's shared-memory opt-in must hold
+    on the second device too (cudaFuncSetAttribute is per device)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import make_docs, make_queries
+
+    from fast_plaid_b200 import search
+
+    docs = make_docs(400, 20, 80, seed=61)
+    queries = make_queries(9, 32, seed=62, docs=docs)
+    one = search.FastPlaid(str(tmp_path / "idx"), device="cuda:0")
+    one.create(docs, kmeans_niters=2)
+    ref = one.search(queries, top_k=10)
+    ref_ts = one.search_token_scores(queries[:3], top_k=3)
+    one.close()
+    both = search.FastPlaid(str(tmp_path / "idx"), device=["cuda:0", "cuda:1"])
+    got = both.search(queries, top_k=10)
+    assert got == ref
+    sub = both.search(queries, top_k=5, subset=list(range(0, 400, 2)))
+    assert all(d % 2 == 0 for r in sub for d, _ in r)
+    ts = both.search_token_scores(queries[:3], top_k=3)
+    for ra, rb in zip(ts, ref_ts):
+        assert [(d, s_) for d, s_, _ in ra] == [(d, s_) for d, s_, _ in rb]
+        assert all(torch.equal(ma, mb) for (_, _, ma), (_, _, mb) in zip(ra, rb))
+    both.close()
