@@ -71,6 +71,17 @@ __device__ __forceinline__ void k3_next_chunk(int32_t* work, int B, int* s_b, in
   __syncthreads();
 }
 
+// Exact pass over a refine list: the bound pass has long moved on, so query b's S slice (K x Qp fp16, 16.8 MB at
+// cfg-3) is no longer in L2 and every first touch of a row would be an isolated HBM miss.  The chunks of a query start
+// together across the CTAs; each streams its share of the slice into L2 before walking its documents.
+__device__ __forceinline__ void k3_prefetch_slice(const __half* Sb, size_t slice_bytes, int chunk, int n_chunks) {
+  const size_t per = ((slice_bytes + n_chunks - 1) / n_chunks + 127) & ~size_t(127);
+  const size_t lo = size_t(chunk) * per;
+  const char* base = reinterpret_cast<const char*>(Sb);
+  for (size_t off = lo + size_t(threadIdx.x) * 128; off < lo + per && off < slice_bytes; off += size_t(blockDim.x) * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
 // maxima of the four half2 registers across the lane groups, then the fp32 sum over the real query tokens
 // (sum_dim_intlist(.., Kind::Float), search.rs:401).  The order of the additions is part of the contract between
 // the bound pass and the exact pass: both call this.
@@ -135,6 +146,7 @@ k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* 
     if (b < 0) break;
     const int n = list ? n_list[b] : n_cand[b];
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP);
+    if (list) k3_prefetch_slice(S + int64_t(b) * K * QP, size_t(K) * QP * 2, s_c, work[b + 1] - work[b]);
     const int32_t* cb = cand + int64_t(b) * cand_cap;
     const int32_t* lb = list ? list + int64_t(b) * cand_cap : nullptr;
     float* ab = approx + int64_t(b) * cand_cap;
@@ -216,6 +228,7 @@ k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64
     if (b < 0) break;
     const int n = list ? n_list[b] : n_cand[b];
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP) + sub;
+    if (list) k3_prefetch_slice(S + int64_t(b) * K * QP, size_t(K) * QP * 2, s_c, work[b + 1] - work[b]);
     const int32_t* cb = cand + int64_t(b) * cand_cap;
     const int32_t* lb = list ? list + int64_t(b) * cand_cap : nullptr;
     float* ab = approx + int64_t(b) * cand_cap;
@@ -489,7 +502,7 @@ __device__ __forceinline__ unsigned k3_push(uint32_t word, uint32_t code, uint32
   return mask;
 }
 
-template <int LPR, int MINB, int W, int U, bool FULLQ>
+template <int LPR, int MINB, int W, int U, bool FULLQ, bool PAIR>
 __global__ void __launch_bounds__(K3_THREADS, MINB)
 k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* __restrict__ doc_offsets,
                 const int32_t* __restrict__ codes, const int32_t* __restrict__ cand, int cand_cap,
@@ -572,6 +585,11 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
     }
     uint32_t head = 0, tail = 0;
     __half2 m0 = sentinel, m1 = sentinel, m2 = sentinel, m3 = sentinel;
+    // PAIR: the end-of-document work (maxima across the lane groups, two column sums) is done for two documents at
+    // once -- the first of a pair is parked in a0..a3, then the lower half of the warp finishes one document and the
+    // upper half the other: half the shuffles, conversions and additions per document
+    __half2 a0 = sentinel, a1 = sentinel, a2 = sentinel, a3 = sentinel;
+    int slot_a = -1;
 
     for (;;) {
       // ---- the next group: same document or the next slot; its code loads go out now ----
@@ -648,20 +666,50 @@ k3_bound_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* _
         }
         rows += tail;
         toks += unsigned(len);
-        k3_reduce_groups<LPR>(m0, m1, m2, m3);
+        const uint4 tq = __ldg(tqp);
+        const int col0 = sub * 8;
         // lower bound: the maxima over the gathered rows; upper bound: unresolved columns raised to tau.  Both sums
         // use the exact kernel's order, fp32 addition is monotone, so lb <= approx <= ub; when no column was raised
         // the two are the same additions of the same values, and whenever lb == ub the score is pinned between them:
         // "resolved" needs no flag, it IS lb == ub.
-        const uint4 tq = __ldg(tqp);
-        const int col0 = sub * 8;
-        const float lb = k3_sum_columns<LPR, FULLQ>(m0, m1, m2, m3, col0, Q);
-        const float ub = k3_sum_columns<LPR, FULLQ>(__hmax2(m0, u32_as_half2(tq.x)), __hmax2(m1, u32_as_half2(tq.y)),
-                                                    __hmax2(m2, u32_as_half2(tq.z)), __hmax2(m3, u32_as_half2(tq.w)),
-                                                    col0, Q);
-        if (lane == 0) {
-          ub_chunk[slot] = ub;
-          lb_chunk[slot] = lb;
+        if (PAIR && LPR <= 8 && slot_a < 0 && nlen >= 0) {
+          a0 = m0; a1 = m1; a2 = m2; a3 = m3;  // park: the next document completes the pair
+          slot_a = slot;
+        } else if (PAIR && LPR <= 8 && slot_a >= 0) {
+          const bool up = lane >= 16;  // lower half: the parked document, upper half: this one
+          __half2 x0 = up ? m0 : a0, x1 = up ? m1 : a1, x2 = up ? m2 : a2, x3 = up ? m3 : a3;
+          const __half2 y0 = up ? a0 : m0, y1 = up ? a1 : m1, y2 = up ? a2 : m2, y3 = up ? a3 : m3;
+          x0 = __hmax2(x0, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(y0), 16)));
+          x1 = __hmax2(x1, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(y1), 16)));
+          x2 = __hmax2(x2, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(y2), 16)));
+          x3 = __hmax2(x3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(y3), 16)));
+#pragma unroll
+          for (int off = LPR; off < 16; off <<= 1) {
+            x0 = __hmax2(x0, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(x0), off)));
+            x1 = __hmax2(x1, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(x1), off)));
+            x2 = __hmax2(x2, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(x2), off)));
+            x3 = __hmax2(x3, u32_as_half2(__shfl_xor_sync(0xffffffffu, half2_as_u32(x3), off)));
+          }
+          const float lb = k3_sum_columns<LPR, FULLQ>(x0, x1, x2, x3, col0, Q);
+          const float ub = k3_sum_columns<LPR, FULLQ>(__hmax2(x0, u32_as_half2(tq.x)), __hmax2(x1, u32_as_half2(tq.y)),
+                                                      __hmax2(x2, u32_as_half2(tq.z)), __hmax2(x3, u32_as_half2(tq.w)),
+                                                      col0, Q);
+          if ((lane & 15) == 0) {
+            const int at = up ? slot : slot_a;
+            ub_chunk[at] = ub;
+            lb_chunk[at] = lb;
+          }
+          slot_a = -1;
+        } else {
+          k3_reduce_groups<LPR>(m0, m1, m2, m3);
+          const float lb = k3_sum_columns<LPR, FULLQ>(m0, m1, m2, m3, col0, Q);
+          const float ub = k3_sum_columns<LPR, FULLQ>(__hmax2(m0, u32_as_half2(tq.x)), __hmax2(m1, u32_as_half2(tq.y)),
+                                                      __hmax2(m2, u32_as_half2(tq.z)), __hmax2(m3, u32_as_half2(tq.w)),
+                                                      col0, Q);
+          if (lane == 0) {
+            ub_chunk[slot] = ub;
+            lb_chunk[slot] = lb;
+          }
         }
         if (nlen < 0) break;  // no further document for this warp in the chunk
         head = tail = 0;
@@ -1202,13 +1250,10 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
     int minb, wq;
     constexpr int TPI = 32 / LPR;
     const bool fullq = L.Q == L.Qp;
-#define K3_BOUND(MB, WW, UU) (fullq ? k3_bound_kernel<LPR, MB, WW, UU, true> : k3_bound_kernel<LPR, MB, WW, UU, false>)
+#define K3_BOUND(MB, WW, UU, PP) (fullq ? k3_bound_kernel<LPR, MB, WW, UU, true, PP> : k3_bound_kernel<LPR, MB, WW, UU, false, PP>)
     switch (shape) {
-      case 1: kern = K3_BOUND(5, 6, 4); minb = 5; wq = K3_WQ_FOR(6, 4 * TPI); break;
-      case 2: kern = K3_BOUND(5, 6, 2); minb = 5; wq = K3_WQ_FOR(6, 2 * TPI); break;
-      case 3: kern = K3_BOUND(6, 6, 2); minb = 6; wq = K3_WQ_FOR(6, 2 * TPI); break;
-      case 4: kern = K3_BOUND(4, 6, 2); minb = 4; wq = K3_WQ_FOR(6, 2 * TPI); break;
-      default: kern = K3_BOUND(4, 6, 4); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
+      case 1: kern = K3_BOUND(4, 6, 4, false); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;  // one document per epilogue (A/B)
+      default: kern = K3_BOUND(4, 6, 4, true); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
     }
 #undef K3_BOUND
     const size_t smem = size_t(L.hb_words + 4) * 4 + size_t(K3_THREADS / 32 + 1) * wq * 4;  // + alignment slack of the rings
