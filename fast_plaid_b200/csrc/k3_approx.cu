@@ -1242,20 +1242,15 @@ int launch_k3_t(const fpb_index* ix, const Ws& ws, int flags, cudaStream_t st) {
   FPB_LAUNCH_CHECK("k3_prefix");
   {
     // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)
-    // shape of the walk: W 32-token windows per group (all their code loads in flight at once, the next group's
-    // prefetched), U gathers per lane and batch.  FPB_K3_SHAPE picks one of the compiled shapes (tuning).
-    static const int shape = getenv("FPB_K3_SHAPE") ? atoi(getenv("FPB_K3_SHAPE")) : 0;
-    void (*kern)(const __half*, int64_t, int, const int64_t*, const int32_t*, const int32_t*, int, const int32_t*,
-                 int32_t*, int, const __half*, const uint32_t*, int, float*, float*, unsigned long long*);
-    int minb, wq;
+    // shape of the walk: 6 32-token windows per group (all their code loads in flight at once, the next group's
+    // prefetched), 4 gathers per lane and batch, 4 CTAs per SM at 64 registers, paired epilogues.  Measured
+    // alternatives (profiles/r02_summary.md): 4 / 8 / 11 / 12 windows, 2 / 8 gathers, 5-6 CTAs at 48 / 40 registers,
+    // one document per epilogue -- all within 3 % or slower.
     constexpr int TPI = 32 / LPR;
+    constexpr int W = 6, U = 4, MINB = 4;
     const bool fullq = L.Q == L.Qp;
-#define K3_BOUND(MB, WW, UU, PP) (fullq ? k3_bound_kernel<LPR, MB, WW, UU, true, PP> : k3_bound_kernel<LPR, MB, WW, UU, false, PP>)
-    switch (shape) {
-      case 1: kern = K3_BOUND(4, 6, 4, false); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;  // one document per epilogue (A/B)
-      default: kern = K3_BOUND(4, 6, 4, true); minb = 4; wq = K3_WQ_FOR(6, 4 * TPI); break;
-    }
-#undef K3_BOUND
+    auto kern = fullq ? k3_bound_kernel<LPR, MINB, W, U, true, true> : k3_bound_kernel<LPR, MINB, W, U, false, true>;
+    const int minb = MINB, wq = K3_WQ_FOR(W, U * TPI);
     const size_t smem = size_t(L.hb_words + 4) * 4 + size_t(K3_THREADS / 32 + 1) * wq * 4;  // + alignment slack of the rings
     FPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     // resident CTAs per SM: limited by the bitmap (228 KB of shared memory per SM, 1 KB reserved per CTA)

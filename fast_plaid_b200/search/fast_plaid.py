@@ -390,6 +390,21 @@ class FastPlaid:
         from ..index import update as _update
 
         with self.lock:
+            # an index last updated by the reference may carry its buffer of recent raw documents (the most recent
+            # ones, fast_plaid.py:1084-1091): trim it like the reference does (:1118-1145) so that a later update by
+            # either implementation does not resurrect deleted documents
+            buffer_path = os.path.join(self.index, "buffer.npy")
+            if os.path.exists(buffer_path) and _delete_buffer:
+                n_docs = read_num_documents(self.index)
+                buf = np.load(buffer_path, allow_pickle=True)
+                start = n_docs - len(buf)
+                drop_b = {i - start for i in subset if start <= i < n_docs}
+                if drop_b:
+                    keep_b = [torch.from_numpy(buf[i]) for i in range(len(buf)) if i not in drop_b]
+                    if keep_b:
+                        save_list_tensors_on_disk(buffer_path, keep_b)
+                    else:
+                        os.remove(buffer_path)
             _update.delete_from_index(self.index, subset, device=self.devices[0])
             if os.path.exists(os.path.join(self.index, "metadata.db")) and _delete_metadata:
                 from ..filtering import delete as _meta_delete
@@ -423,7 +438,8 @@ class FastPlaid:
     @staticmethod
     def _as_query_tensor(queries_embeddings) -> torch.Tensor:
         """A list of [Q_i, D] (or [1, Q_i, D]) tensors becomes one zero-padded [B, Qmax, D] tensor
-        (fast_plaid.py:772-780); zero rows score 0 against everything and never probe."""
+        (fast_plaid.py:772-780).  A zero row scores 0 against every centroid, so -- exactly as in the reference --
+        its "best" centroids are the first n_ivf_probe ones by the tie rule and it adds 0 to every document score."""
         if not isinstance(queries_embeddings, list):
             return queries_embeddings
         rows = [q.squeeze(0) if q.dim() == 3 else q for q in queries_embeddings]

@@ -214,3 +214,20 @@ def test_create_refuses_what_the_engine_cannot_search(tmp_path):
     with pytest.raises(ValueError, match="nbits"):
         fp.create(make_docs(5, 5, 10, seed=14), kmeans_niters=1, nbits=8)
     assert not os.path.exists(os.path.join(str(tmp_path / "idx"), "metadata.json"))
+
+
+def test_delete_trims_a_reference_written_buffer(tmp_path):
+    """fast_plaid.py:1118-1145 of the reference: `buffer.npy` holds the raw embeddings of the most recent documents;
+    deleting some of them must remove their entries."""
+    import numpy as np
+
+    path = str(tmp_path / "idx")
+    fp = search.FastPlaid(path, device="cpu")
+    docs = make_docs(40, 5, 12, seed=21)
+    fp.create(docs, kmeans_niters=1)
+    search.fast_plaid.save_list_tensors_on_disk(os.path.join(path, "buffer.npy"), docs[-5:])  # docs 35..39
+    fp.delete([3, 36, 39])
+    buf = np.load(os.path.join(path, "buffer.npy"), allow_pickle=True)
+    assert len(buf) == 3 and np.array_equal(buf[0], docs[35].numpy()) and np.array_equal(buf[2], docs[38].numpy())
+    fp.delete([32, 33, 34])  # the three remaining buffer documents are now ids 32..34
+    assert not os.path.exists(os.path.join(path, "buffer.npy"))
