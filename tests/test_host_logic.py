@@ -229,5 +229,5 @@ def test_delete_trims_a_reference_written_buffer(tmp_path):
     fp.delete([3, 36, 39])
     buf = np.load(os.path.join(path, "buffer.npy"), allow_pickle=True)
     assert len(buf) == 3 and np.array_equal(buf[0], docs[35].numpy()) and np.array_equal(buf[2], docs[38].numpy())
-    fp.delete([32, 33, 34])  # the three remaining buffer documents are now ids 32..34
+    fp.delete([34, 35, 36])  # the three remaining buffer documents are now the last three ids, 34..36
     assert not os.path.exists(os.path.join(path, "buffer.npy"))
