@@ -71,17 +71,6 @@ __device__ __forceinline__ void k3_next_chunk(int32_t* work, int B, int* s_b, in
   __syncthreads();
 }
 
-// Exact pass over a refine list: the bound pass has long moved on, so query b's S slice (K x Qp fp16, 16.8 MB at
-// cfg-3) is no longer in L2 and every first touch of a row would be an isolated HBM miss.  The chunks of a query start
-// together across the CTAs; each streams its share of the slice into L2 before walking its documents.
-__device__ __forceinline__ void k3_prefetch_slice(const __half* Sb, size_t slice_bytes, int chunk, int n_chunks) {
-  const size_t per = ((slice_bytes + n_chunks - 1) / n_chunks + 127) & ~size_t(127);
-  const size_t lo = size_t(chunk) * per;
-  const char* base = reinterpret_cast<const char*>(Sb);
-  for (size_t off = lo + size_t(threadIdx.x) * 128; off < lo + per && off < slice_bytes; off += size_t(blockDim.x) * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-}
-
 // maxima of the four half2 registers across the lane groups, then the fp32 sum over the real query tokens
 // (sum_dim_intlist(.., Kind::Float), search.rs:401).  The order of the additions is part of the contract between
 // the bound pass and the exact pass: both call this.
@@ -146,7 +135,6 @@ k3_approx_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64_t* 
     if (b < 0) break;
     const int n = list ? n_list[b] : n_cand[b];
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP);
-    if (list) k3_prefetch_slice(S + int64_t(b) * K * QP, size_t(K) * QP * 2, s_c, work[b + 1] - work[b]);
     const int32_t* cb = cand + int64_t(b) * cand_cap;
     const int32_t* lb = list ? list + int64_t(b) * cand_cap : nullptr;
     float* ab = approx + int64_t(b) * cand_cap;
@@ -228,7 +216,6 @@ k3_approx_nsh_kernel(const __half* __restrict__ S, int64_t K, int Q, const int64
     if (b < 0) break;
     const int n = list ? n_list[b] : n_cand[b];
     const uint4* Sb = reinterpret_cast<const uint4*>(S + int64_t(b) * K * QP) + sub;
-    if (list) k3_prefetch_slice(S + int64_t(b) * K * QP, size_t(K) * QP * 2, s_c, work[b + 1] - work[b]);
     const int32_t* cb = cand + int64_t(b) * cand_cap;
     const int32_t* lb = list ? list + int64_t(b) * cand_cap : nullptr;
     float* ab = approx + int64_t(b) * cand_cap;

@@ -10,6 +10,9 @@ if [ "$N" = "2" ]; then
   run cfg3 --no-cpu-baseline
   run cfg5 --config cfg5 --no-cpu-baseline
   run cfg3_par --parity-queries 8
+elif [ "$N" = "4" ]; then
+  run cfg3 --no-cpu-baseline
+  run cfg3_par --parity-queries 4
 else
   run cfg3 --no-cpu-baseline
   run cfg3_g1 --no-cpu-baseline --query-groups 1
