@@ -226,15 +226,9 @@ extern "C" int fpb_search_batch_sharded(const fpb_index* ix, fpb_comm* comm, int
     FPB_TRY(launch_emit_records(ix, ws, recs, st));
   }
   FPB_NCCL_CHECK(nccl().AllGather(recs, all_recs, size_t(per_rank) * 16, ncclUint8, comm->comm, st));
-  // ---- every rank ranks every query: group g's queries come from the records of its n_shards ranks ----
-  for (int g = 0; g < n_query_groups; ++g) {
-    const int g0 = g * b_local;
-    const int gn = B - g0 < 0 ? 0 : (B - g0 < b_local ? B - g0 : b_local);
-    if (gn == 0) break;
-    FPB_TRY(launch_merge(all_recs + int64_t(g) * n_shards * per_rank, n_shards, b_local, gn, R, p->top_k,
-                         d_out_ids + int64_t(g0) * p->top_k, d_out_scores + int64_t(g0) * p->top_k, d_out_counts + g0,
-                         st));
-  }
+  // ---- every rank ranks every query in ONE launch: query q belongs to group q / b_local, whose records are the
+  //      [n_shards, b_local, R] block of that group in the gathered array (launch_merge with n_queries > b_stride) ----
+  FPB_TRY(launch_merge(all_recs, n_shards, b_local, B, R, p->top_k, d_out_ids, d_out_scores, d_out_counts, st));
   return FPB_OK;
 }
 

@@ -101,14 +101,20 @@ __global__ void emit_records_kernel(const float* __restrict__ exact, const float
 //   keep the R best by (approx desc, doc id asc)   -- search.rs:605-619 on the whole index
 //   order them by  (exact desc, doc id asc)        -- search.rs:659
 __global__ void __launch_bounds__(1024)
-k6_merge_kernel(const fpb_record* __restrict__ all, int n_shards, int B, int R, int P, int Rp2, int top_k,
+k6_merge_kernel(const fpb_record* __restrict__ all_groups, int n_shards, int B, int R, int P, int Rp2, int top_k,
                 int64_t* __restrict__ out_ids, float* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);  // [P]
   uint64_t* keys2 = keys + P;                               // [Rp2]
   uint32_t* pay = reinterpret_cast<uint32_t*>(keys2 + Rp2);  // [P] record index carried through the sort
   __shared__ int s_valid;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  // query blockIdx.x of the whole batch = query `b` of query group blockIdx.x / B, whose records are the
+  // [n_shards, B, R] block of that group (one group: the block index is the query)
+  const int b = blockIdx.x % B, tid = threadIdx.x;
+  const fpb_record* all = all_groups + int64_t(blockIdx.x / B) * n_shards * B * R;
+  out_ids += int64_t(blockIdx.x - b) * top_k;
+  out_scores += int64_t(blockIdx.x - b) * top_k;
+  out_counts += blockIdx.x - b;
   const int total = n_shards * R;
   if (tid == 0) s_valid = 0;
   __syncthreads();
@@ -306,11 +312,12 @@ extern "C" int fpb_merge_shards(const fpb_record* d_all_records, int n_shards, i
                       static_cast<cudaStream_t>(stream));
 }
 
-// merge of the first `n_queries` queries of gathered records laid out [n_shards, b_stride, R]
+// merge of `n_queries` queries of gathered records laid out [n_groups][n_shards, b_stride, R]: query q is query
+// q % b_stride of group q / b_stride (n_queries <= b_stride: one group)
 int launch_merge(const fpb_record* d_all_records, int n_shards, int b_stride, int n_queries, int R, int top_k,
                  int64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, cudaStream_t stream) {
   const int B = b_stride;
-  if (!d_all_records || n_shards < 1 || B < 1 || R < 1 || top_k < 1 || n_queries < 0 || n_queries > B) {
+  if (!d_all_records || n_shards < 1 || B < 1 || R < 1 || top_k < 1 || n_queries < 0) {
     fpb_set_error("fpb_merge_shards: bad arguments");
     return FPB_ERR_INVALID;
   }
