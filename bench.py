@@ -603,7 +603,7 @@ def count_launches(world: int, approx: str) -> int:
     hibits, prefix, bound, refine list, prefix, exact; direct: prefix, exact), select, k5, rank; sharded adds the
     key emit, the threshold, the record emit and the merge instead of the rank."""
     k3 = 2 if approx == "direct" else 7
-    return 5 + k3 + 1 + 1 + (1 if world == 1 else 3 + max(1, world // 2))
+    return 5 + k3 + 1 + 1 + (1 if world == 1 else 4)
 
 
 # ----------------------------------------------------------------------------------------
