@@ -83,7 +83,8 @@ extern "C" int fpb_comm_unique_id(void* out_id) {
     return FPB_ERR_INVALID;
   }
   if (!nccl().ok) {
-    fpb_set_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "symbols missing");
+    const char* why = dlerror();
+    fpb_set_error("NCCL (libnccl.so.2) could not be loaded: %s", why ? why : "symbols missing");
     return FPB_ERR_UNSUPPORTED;
   }
   ncclUniqueId id;
