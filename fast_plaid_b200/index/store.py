@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import json
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -128,7 +129,8 @@ def read_index_to_device(index_path: str, device: str | torch.device,
     codes = torch.empty((max(t1 - t0, 0),), dtype=torch.int32, device=dev)
     residuals = torch.empty((max(t1 - t0, 0), pd), dtype=torch.uint8, device=dev)
     c0 = 0  # first token of the chunk in the whole index
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)  # read-only memory maps are only ever read here
         for i in range(num_chunks):
             n_tok = int(sum(chunk_lens[i]))
             a, b = max(c0, t0), min(c0 + n_tok, t1)
