@@ -242,6 +242,23 @@ def traffic_for(config: str, world: int):
         return None, None
 
 
+HBM_INDEX_BUDGET = 60e9  # bytes of one GPU's 180 GB given to index data; the rest is score table, workspace, headroom
+
+
+def default_query_groups(world: int, cfg: dict) -> int:
+    """Grid policy: the FEWEST document shards whose slice fits the per-GPU budget, every other rank a query group.
+    Splitting the queries costs nothing (they are independent; each rank runs K1 / the probe on its own B / groups
+    queries), splitting the documents repeats those stages on every shard and adds the pruning exchange -- measured
+    on cfg3: 2 x 1 beats 1 x 2 by 11 %, 4 x 1 beats 2 x 2 by 6 % (profiles/r02_summary.md).  Documents are sharded
+    when the index needs it (or on request: --query-groups)."""
+    tokens = cfg["n_docs"] * cfg["doc_len"]
+    index_bytes = tokens * (DIM * NBITS // 8 + 4 + 2 + 4)  # residuals, int32 code, fp16 norm, inverted-file entry
+    for n_shards in range(1, world + 1):
+        if world % n_shards == 0 and index_bytes / n_shards <= HBM_INDEX_BUDGET:
+            return world // n_shards
+    return 1
+
+
 # ----------------------------------------------------------------------------------------
 def run_b200(args) -> dict:
     from fast_plaid_b200.engine import FPB_FLAG_APPROX_DIRECT, DeviceIndex, IndexTensors, ShardComm, _check, shard_grid
@@ -256,10 +273,8 @@ def run_b200(args) -> dict:
     torch.cuda.set_device(local)
     cfg = CONFIGS[args.config]
     n_docs = cfg["n_docs"]
-    # the grid of the sharded search: query groups x document shards (csrc/comm.cu).  Default: half the ranks'
-    # worth of query groups from 4 GPUs up (K1 and the probe then run on B / groups queries per GPU), plain document
-    # sharding below.
-    n_groups = args.query_groups or (world // 2 if world >= 4 else 1)
+    # the grid of the sharded search: query groups x document shards (csrc/comm.cu)
+    n_groups = args.query_groups or default_query_groups(world, cfg)
     group, doc_shard, n_shards = shard_grid(rank, world, n_groups)
     lo, hi = (n_docs * doc_shard) // n_shards, (n_docs * (doc_shard + 1)) // n_shards
     synth = load_synthetic_module()
@@ -979,7 +994,8 @@ def main() -> None:
                     help="queries cross-checked against the oracle (rank 0, any number of GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (CPU baseline and parity sample)")
     ap.add_argument("--query-groups", type=int, default=0,
-                    help="sharded runs: query groups of the rank grid (0 = world/2 from 4 GPUs up, else 1)")
+                    help="multi-GPU runs: query groups of the rank grid (0 = as many as the index size allows: fewest document "
+                         "shards that fit the per-GPU budget)")
     ap.add_argument("--approx", choices=["two-pass", "direct"], default="two-pass",
                     help="approximate stage: exact two-pass pruning (default) or the one-pass A/B alternative")
     args = ap.parse_args()
