@@ -45,6 +45,25 @@ def test_bench_configs_cover_the_baseline_configs():
     assert "north_star" in base
 
 
+def test_grid_policy_uses_the_fewest_document_shards_that_fit():
+    """bench.default_query_groups: every rank a query group while the index fits one GPU's budget, document shards
+    (always a divisor of the world size) only when it does not."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from fast_plaid_b200.engine import shard_grid
+
+    for world in (1, 2, 4, 8):
+        assert bench.default_query_groups(world, bench.CONFIGS["cfg3"]) == world
+    big = dict(n_docs=10_000_000, doc_len=300)  # ~220 GB of index data
+    assert bench.default_query_groups(8, big) == 2  # 4 shards of 55 GB, two query groups
+    assert bench.default_query_groups(4, big) == 1
+    assert bench.default_query_groups(2, big) == 1  # does not fit at all: as many shards as there are ranks
+    for world in (2, 4, 8):
+        g = bench.default_query_groups(world, big)
+        cells = {shard_grid(r, world, g)[:2] for r in range(world)}
+        assert len(cells) == world and world % g == 0
+
+
 def test_parity_sample_classifier_on_an_oracle_stand_in():
     """bench.parity_sample, fed the oracle's own results in place of the engine's: nothing to explain, every list
     identical; and with one returned document swapped for a far-away one it must report the mismatch."""
